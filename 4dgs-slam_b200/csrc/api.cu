@@ -1,0 +1,187 @@
+// api.cu -- extern "C" entry points declared in include/g4r.h.
+#include "g4r_common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+static thread_local char g_err[512] = "";
+
+int g4r_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct G4RContext {
+    int32_t* host_n;        // pinned
+    cudaEvent_t ev;
+    bool pending;
+    int renders_since_project;   // > 0: the scatter cursors of the current image state are dirty
+};
+
+static int check_frame(const G4RFrame* f, bool backward) {
+    if (!f) return g4r_set_error(G4R_EINVAL, "frame is NULL");
+    if (f->width <= 0 || f->height <= 0) return g4r_set_error(G4R_EINVAL, "image size %dx%d is not positive", f->width, f->height);
+    if (!f->bg || !f->viewmatrix || !f->projmatrix || !f->campos) return g4r_set_error(G4R_EINVAL, "bg/viewmatrix/projmatrix/campos must be device pointers");
+    if (backward && !f->projmatrix_raw) return g4r_set_error(G4R_EINVAL, "projmatrix_raw is required for backward");
+    if (f->sh_degree < 0 || f->sh_degree > 3) return g4r_set_error(G4R_EINVAL, "sh_degree %d outside 0..3", f->sh_degree);
+    return G4R_OK;
+}
+
+static int check_gaussians(const G4RFrame* f, const G4RGaussians* g) {
+    if (!g) return g4r_set_error(G4R_EINVAL, "gaussians is NULL");
+    if (g->P < 0) return g4r_set_error(G4R_EINVAL, "P is negative");
+    if (g->P == 0) return G4R_OK;
+    if (!g->means3D || !g->opacities) return g4r_set_error(G4R_EINVAL, "means3D and opacities are required");
+    if ((g->shs == nullptr) == (g->colors_precomp == nullptr))
+        return g4r_set_error(G4R_EINVAL, "Please provide excatly one of either SHs or precomputed colors!");
+    const bool has_sr = g->scales != nullptr && g->rotations != nullptr;
+    if (((g->scales == nullptr) != (g->rotations == nullptr)) || (has_sr == (g->cov3D_precomp != nullptr)))
+        return g4r_set_error(G4R_EINVAL, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    if (g->shs) {
+        const int K = (f->sh_degree + 1) * (f->sh_degree + 1);
+        if (f->sh_coeffs < K) return g4r_set_error(G4R_EINVAL, "sh_degree %d needs %d coefficients but sh has %d", f->sh_degree, K, f->sh_coeffs);
+    }
+    return G4R_OK;
+}
+
+extern "C" {
+
+const char* g4r_last_error(void) { return g_err; }
+int g4r_version(void) { return 1; }
+
+int g4r_context_create(G4RContext** out) {
+    if (!out) return g4r_set_error(G4R_EINVAL, "out is NULL");
+    G4RContext* c = new (std::nothrow) G4RContext();
+    if (!c) return g4r_set_error(G4R_EINVAL, "out of host memory");
+    c->host_n = nullptr; c->ev = nullptr; c->pending = false; c->renders_since_project = 0;
+    cudaError_t e = cudaMallocHost((void**)&c->host_n, sizeof(int32_t) * 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        if (c->host_n) cudaFreeHost(c->host_n);
+        delete c;
+        return g4r_set_error(G4R_ECUDA, "context creation failed: %s", cudaGetErrorString(e));
+    }
+    c->host_n[0] = 0;
+    *out = c;
+    return G4R_OK;
+}
+
+void g4r_context_destroy(G4RContext* c) {
+    if (!c) return;
+    if (c->ev) cudaEventDestroy(c->ev);
+    if (c->host_n) cudaFreeHost(c->host_n);
+    delete c;
+}
+
+size_t g4r_geom_bytes(int32_t P) { return GeomLayout(P < 0 ? 0 : P).total; }
+size_t g4r_image_bytes(int32_t W, int32_t H) { return ImageLayout(W < 1 ? 1 : W, H < 1 ? 1 : H).total; }
+size_t g4r_binning_bytes(int64_t capacity) { return BinLayout(capacity).total; }
+size_t g4r_backward_scratch_bytes(int32_t P) { return g4r_align((size_t)(P < 1 ? 1 : P) * G4R_ACC_STRIDE * sizeof(float)) + 256; }
+
+int g4r_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, G4RLayout* out) {
+    if (!out) return g4r_set_error(G4R_EINVAL, "out is NULL");
+    const GeomLayout gl(P < 0 ? 0 : P);
+    const ImageLayout il(W < 1 ? 1 : W, H < 1 ? 1 : H);
+    const BinLayout bl(capacity);
+    out->geom_rec = gl.rec; out->geom_clamped = gl.clamped;
+    out->img_final_T = il.final_T; out->img_n_contrib = il.n_contrib; out->img_ranges = il.ranges;
+    out->img_counts = il.counts; out->img_header = il.header;
+    out->bin_point_list = bl.point_list; out->bin_pairs = bl.pairs;
+    return G4R_OK;
+}
+
+int g4r_forward_project(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g, void* geom, void* img, int32_t* radii,
+                        int32_t* n_touched, void* stream) {
+    int rc;
+    if (!ctx) return g4r_set_error(G4R_EINVAL, "context is NULL");
+    if ((rc = check_frame(f, false)) != G4R_OK) return rc;
+    if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
+    if (!img) return g4r_set_error(G4R_EINVAL, "img buffer is NULL");
+    if (g->P > 0 && (!geom || !radii || !n_touched)) return g4r_set_error(G4R_EINVAL, "geom/radii/n_touched buffers are NULL");
+    if (((uintptr_t)geom | (uintptr_t)img) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const ImageLayout il(f->width, f->height);
+    char* ib = (char*)img;
+    // header, per-tile counts and scatter cursors are contiguous at the start of the image state
+    G4R_CUDA_OK(cudaMemsetAsync(ib + il.header, 0, il.ranges - il.header, s));
+    if (g->P > 0) {
+        if ((rc = launch_project(*f, *g, geom, img, radii, n_touched, s)) != G4R_OK) return rc;
+    }
+    if ((rc = launch_tile_scan(*f, img, s)) != G4R_OK) return rc;
+    G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    G4R_CUDA_OK(cudaEventRecord(ctx->ev, s));
+    ctx->pending = true;
+    ctx->renders_since_project = 0;
+    return G4R_OK;
+}
+
+int64_t g4r_wait_num_rendered(G4RContext* ctx) {
+    if (!ctx) return g4r_set_error(G4R_EINVAL, "context is NULL");
+    if (!ctx->pending) return g4r_set_error(G4R_EINVAL, "g4r_wait_num_rendered without a preceding g4r_forward_project");
+    cudaError_t e = cudaEventSynchronize(ctx->ev);
+    if (e != cudaSuccess) return g4r_set_error(G4R_ECUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+    ctx->pending = false;
+    return (int64_t)(uint32_t)ctx->host_n[0];
+}
+
+int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g, void* geom, void* img, void* binning,
+                       int64_t capacity, const G4RForwardOut* out, void* stream) {
+    int rc;
+    if (!ctx) return g4r_set_error(G4R_EINVAL, "context is NULL");
+    if ((rc = check_frame(f, false)) != G4R_OK) return rc;
+    if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
+    if (!out || !out->color || !out->depth || !out->opacity) return g4r_set_error(G4R_EINVAL, "output images are NULL");
+    if (!img || !binning) return g4r_set_error(G4R_EINVAL, "img/binning buffers are NULL");
+    if (g->P > 0 && (!geom || !out->radii || !out->n_touched)) return g4r_set_error(G4R_EINVAL, "geom/radii/n_touched are NULL");
+    if (capacity < 0) return g4r_set_error(G4R_EINVAL, "capacity is negative");
+    if (((uintptr_t)geom | (uintptr_t)img | (uintptr_t)binning) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g->P > 0) {
+        if (ctx->renders_since_project > 0) {
+            // re-run after a capacity overflow: the aborted attempt touched nothing (every phase-2 kernel
+            // exits when N > capacity), but be robust to a caller re-rendering a completed frame too.
+            const ImageLayout il(f->width, f->height);
+            G4R_CUDA_OK(cudaMemsetAsync((char*)img + il.cursors, 0, (size_t)il.tiles * 4, s));
+            G4R_CUDA_OK(cudaMemsetAsync(out->n_touched, 0, sizeof(int32_t) * (size_t)g->P, s));
+        }
+        ctx->renders_since_project++;
+        if ((rc = launch_scatter_sort(*f, g->P, out->radii, geom, img, binning, capacity, s)) != G4R_OK) return rc;
+    }
+    return launch_composite_forward(*f, g->P, geom, img, binning, capacity, *out, s);
+}
+
+int g4r_backward(const G4RFrame* f, const G4RGaussians* g, const int32_t* radii, const void* geom, const void* img,
+                 const void* binning, void* scratch, const G4RBackwardIO* io, void* stream) {
+    int rc;
+    if ((rc = check_frame(f, true)) != G4R_OK) return rc;
+    if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
+    if (!io || !io->dL_dtau) return g4r_set_error(G4R_EINVAL, "io / dL_dtau is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    G4R_CUDA_OK(cudaMemsetAsync(io->dL_dtau, 0, sizeof(float) * 8, s));
+    if (g->P == 0) return G4R_OK;
+    if (!io->dL_dcolor || !io->dL_ddepth) return g4r_set_error(G4R_EINVAL, "dL_dcolor / dL_ddepth are NULL");
+    if (!io->dL_dmeans3D || !io->dL_dmeans2D || !io->dL_dopacity) return g4r_set_error(G4R_EINVAL, "dL_dmeans3D/dL_dmeans2D/dL_dopacity are NULL");
+    if (g->shs && !io->dL_dshs) return g4r_set_error(G4R_EINVAL, "dL_dshs is NULL although shs was given");
+    if (!radii || !geom || !img || !binning || !scratch) return g4r_set_error(G4R_EINVAL, "saved state / scratch is NULL");
+    if (((uintptr_t)geom | (uintptr_t)img | (uintptr_t)binning | (uintptr_t)scratch) & 15u)
+        return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    if (io->dL_drotations && ((uintptr_t)io->dL_drotations & 15u)) return g4r_set_error(G4R_EINVAL, "dL_drotations must be 16-byte aligned");
+    float* acc = (float*)scratch;
+    G4R_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)g->P * G4R_ACC_STRIDE * sizeof(float), s));
+    if ((rc = launch_composite_backward(*f, g->P, geom, img, binning, io->dL_dcolor, io->dL_ddepth, acc, s)) != G4R_OK) return rc;
+    return launch_gaussian_backward(*f, *g, radii, geom, acc, *io, s);
+}
+
+int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present, void* stream) {
+    (void)projmatrix;   // the reference's frustum test only uses the view-space depth (auxiliary.h:154)
+    if (P < 0) return g4r_set_error(G4R_EINVAL, "P is negative");
+    if (P == 0) return G4R_OK;
+    if (!means3D || !viewmatrix || !present) return g4r_set_error(G4R_EINVAL, "NULL argument");
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+}  // extern "C"

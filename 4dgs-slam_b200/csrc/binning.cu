@@ -1,0 +1,224 @@
+// binning.cu -- tile binning: per-tile offsets, instance scatter, per-tile (depth,id) sort.
+//
+// Replaces the reference's global binning pipeline (DGR/cuda_rasterizer/rasterizer_impl.cu):
+//   cub::DeviceScan::InclusiveSum over P Gaussians            (:280)
+//   blocking D2H copy of num_rendered                          (:284)
+//   duplicateWithKeys                                           (:70-111, :292)
+//   cub::DeviceRadixSort::SortPairs on 64-bit (tile|depth) keys (:306-311)  <- 6 HBM passes
+//   cudaMemset(ranges) + identifyTileRanges                     (:313-321)
+// with a two-level scheme that never sorts across tiles:
+//   1. project_kernel already histogrammed instances per TILE (project.cu);
+//   2. tile_scan_kernel: exclusive scan over the (few thousand) tiles -> ranges[tile] and N;
+//   3. scatter_kernel: each visible Gaussian drops (depth bits, id) into its tiles' segments;
+//   4. tile_sort_kernel: one CTA per tile sorts its segment by the 64-bit key (depth<<32 | id)
+//      entirely in shared memory and emits the sorted ids.
+// Result equivalence: the reference sorts keys (tile<<32 | depth bits) with a STABLE radix sort
+// over values emitted in increasing Gaussian id, so inside a tile instances are ordered by
+// (depth bits, id).  Sorting each tile segment by (depth bits, id) gives the identical
+// point_list; ranges[t] = [start,end) is identical by construction, (0,0) for empty tiles
+// exactly like the reference's memset + identifyTileRanges.
+#include "g4r_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// 2. exclusive scan over tiles (single CTA; tiles <= a few 10^4)
+// ---------------------------------------------------------------------------------------------
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(const uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
+                                                                 uint32_t* __restrict__ header, int tiles) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    const int per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int t0 = threadIdx.x * per, t1 = min(tiles, t0 + per);
+    uint32_t sum = 0;
+    for (int t = t0; t < t1; ++t) sum += counts[t];
+    // block-wide exclusive scan of `sum`
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        s_warp[lane] = wi - w;                  // exclusive prefix of the warp totals
+        if (lane == 31) header[0] = wi;         // N = total number of (tile, Gaussian) instances
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t c = counts[t];
+        ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+        run += c;
+    }
+}
+
+int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
+    const ImageLayout il(f.width, f.height);
+    char* b = (char*)img;
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((const uint32_t*)(b + il.counts), (uint2*)(b + il.ranges),
+                                                (uint32_t*)(b + il.header), il.tiles);
+    G4R_LAUNCH_OK("tile_scan_kernel");
+    return G4R_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. scatter (depth bits, id) into tile segments
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
+                                                            const uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
+                                                            uint2* __restrict__ pairs,
+                                                            const uint32_t* __restrict__ header, uint32_t capacity,
+                                                            uint32_t gx, uint32_t gy) {
+    if (header[0] > capacity) return;           // uniform: caller re-runs phase 2 with a larger buffer
+    const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
+    if (i >= P) return;
+    const int radius = radii[i];
+    if (radius <= 0) return;
+    const float4 a = ldg4(rec + (size_t)i * 3);
+    const float4 b = ldg4(rec + (size_t)i * 3 + 1);
+    const TileRect r = tile_rect(a.x, a.y, radius, gx, gy);
+    const uint32_t key = __float_as_uint(b.z);  // depth bits, as duplicateWithKeys packs them (:104)
+    for (uint32_t ty = r.y0; ty < r.y1; ++ty)
+        for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
+            const uint32_t t = ty * gx + tx;
+            const uint32_t slot = __ldg(&ranges[t].x) + atomicAdd(cursors + t, 1u);   // cursors start at 0
+            pairs[slot] = make_uint2(key, (uint32_t)i);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. per-tile sort by (depth bits, id)
+// ---------------------------------------------------------------------------------------------
+#define SORT_SMEM_MAX 4096                      // 32 KB of 64-bit keys
+
+// Stable LSD radix pass over one tile segment living in global memory (rare, oversized tiles).
+static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, uint32_t* __restrict__ out_ids) {
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_base[256];
+    __shared__ int s_skip;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint2* src = a;
+    uint2* dst = b;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = (pass & 3) * 8;
+        const bool hi = pass >= 4;              // passes 0-3: id (secondary key); 4-7: depth bits (primary)
+        s_hist[tid] = 0;
+        if (tid == 0) s_skip = 0;
+        __syncthreads();
+        for (uint32_t e = tid; e < L; e += G4R_BLOCK) {
+            const uint2 kv = src[e];
+            atomicAdd(&s_hist[((hi ? kv.x : kv.y) >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (s_hist[tid] == L) s_skip = 1;       // every key shares this digit: pass is the identity
+        __syncthreads();
+        if (s_skip) { __syncthreads(); continue; }
+        // exclusive scan of the 256 bins
+        {
+            const uint32_t c = s_hist[tid];
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            __shared__ uint32_t s_w[8];
+            if (lane == 31) s_w[warp] = incl;
+            __syncthreads();
+            uint32_t off = 0;
+            for (int w = 0; w < warp; ++w) off += s_w[w];
+            s_base[tid] = off + incl - c;
+        }
+        __syncthreads();
+        // ordered scatter: chunks of 256 in segment order, warps take turns inside a chunk
+        for (uint32_t c0 = 0; c0 < L; c0 += G4R_BLOCK) {
+            const uint32_t e = c0 + tid;
+            const bool valid = e < L;
+            uint2 kv = make_uint2(0u, 0u);
+            uint32_t digit = 0;
+            if (valid) { kv = src[e]; digit = ((hi ? kv.x : kv.y) >> shift) & 255u; }
+            const uint32_t act = __ballot_sync(0xffffffffu, valid);
+            uint32_t peers = 0, rank = 0;
+            if (valid) {
+                peers = __match_any_sync(act, digit);
+                rank = __popc(peers & ((1u << lane) - 1u));
+            }
+            for (int w = 0; w < G4R_BLOCK / 32; ++w) {
+                if (warp == w && valid) {
+                    uint32_t off = 0;
+                    const int leader = __ffs(peers) - 1;
+                    if (lane == leader) { off = s_base[digit]; s_base[digit] = off + __popc(peers); }
+                    off = __shfl_sync(peers, off, leader);
+                    dst[off + rank] = kv;
+                }
+                __syncthreads();
+            }
+        }
+        uint2* t = src; src = dst; dst = t;
+        __syncthreads();
+    }
+    for (uint32_t e = tid; e < L; e += G4R_BLOCK) out_ids[e] = src[e].y;
+}
+
+__global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __restrict__ ranges, uint2* __restrict__ pairs,
+                                                              uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list,
+                                                              const uint32_t* __restrict__ header, uint32_t capacity) {
+    if (header[0] > capacity) return;
+    __shared__ unsigned long long s_key[SORT_SMEM_MAX];
+    const uint2 range = ranges[blockIdx.x];
+    const uint32_t L = range.y - range.x;
+    if (L == 0) return;
+    const int tid = threadIdx.x;
+    if (L == 1) { if (tid == 0) point_list[range.x] = pairs[range.x].y; return; }
+    if (L > SORT_SMEM_MAX) { big_tile_sort(pairs + range.x, pairs_alt + range.x, L, point_list + range.x); return; }
+
+    uint32_t n = 32;
+    while (n < L) n <<= 1;
+    for (uint32_t e = tid; e < n; e += G4R_BLOCK) {
+        unsigned long long k = ~0ull;            // padding sorts to the end
+        if (e < L) { const uint2 kv = pairs[range.x + e]; k = ((unsigned long long)kv.x << 32) | kv.y; }
+        s_key[e] = k;
+    }
+    __syncthreads();
+    // bitonic network over n = 2^m keys; n/2 comparators per stage spread over the CTA
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < (n >> 1); t += G4R_BLOCK) {
+                const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t hi = lo | j;
+                const unsigned long long x = s_key[lo], y = s_key[hi];
+                const bool up = (lo & k) == 0;
+                if ((x > y) == up) { s_key[lo] = y; s_key[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t e = tid; e < L; e += G4R_BLOCK) point_list[range.x + e] = (uint32_t)s_key[e];
+}
+
+int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
+                        int64_t capacity, cudaStream_t s) {
+    const GeomLayout gl(P);
+    const ImageLayout il(f.width, f.height);
+    const BinLayout bl(capacity);
+    char* ib = (char*)img;
+    char* bb = (char*)binning;
+    const uint32_t cap = (uint32_t)(capacity > 0xffffffffll ? 0xffffffffll : capacity);
+    const float4* rec = (const float4*)((const char*)geom + gl.rec);
+    scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
+                                                                         (uint32_t*)(ib + il.cursors), (uint2*)(bb + bl.pairs), (const uint32_t*)(ib + il.header),
+                                                                         cap, (uint32_t)il.tiles_x, (uint32_t)il.tiles_y);
+    G4R_LAUNCH_OK("scatter_kernel");
+    tile_sort_kernel<<<il.tiles, G4R_BLOCK, 0, s>>>((const uint2*)(ib + il.ranges), (uint2*)(bb + bl.pairs), (uint2*)(bb + bl.pairs_alt),
+                                                    (uint32_t*)(bb + bl.point_list), (const uint32_t*)(ib + il.header), cap);
+    G4R_LAUNCH_OK("tile_sort_kernel");
+    return G4R_OK;
+}

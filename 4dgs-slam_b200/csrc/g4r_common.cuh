@@ -1,0 +1,125 @@
+// g4r_common.cuh -- shared device helpers + scratch layouts for the sm_100a rasterizer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/g4r.h"
+
+#define G4R_BLOCK 256              // threads per CTA for every kernel in this library
+#define G4R_TILE_PIX (G4R_TILE * G4R_TILE)
+#define G4R_HEADER_WORDS 8
+
+// SH basis constants (values identical to DGR/cuda_rasterizer/auxiliary.h:22-39 and
+// gaussian_splatting/utils/sh_utils.py:24-41 -- they are the real SH normalisation constants).
+#define G4R_SH_C0 0.28209479177387814f
+#define G4R_SH_C1 0.4886025119029199f
+#define G4R_SH_C2_0 1.0925484305920792f
+#define G4R_SH_C2_1 (-1.0925484305920792f)
+#define G4R_SH_C2_2 0.31539156525252005f
+#define G4R_SH_C2_3 (-1.0925484305920792f)
+#define G4R_SH_C2_4 0.5462742152960396f
+#define G4R_SH_C3_0 (-0.5900435899266435f)
+#define G4R_SH_C3_1 2.890611442640554f
+#define G4R_SH_C3_2 (-0.4570457994644658f)
+#define G4R_SH_C3_3 0.3731763325901154f
+#define G4R_SH_C3_4 (-0.4570457994644658f)
+#define G4R_SH_C3_5 1.445305721320277f
+#define G4R_SH_C3_6 (-0.5900435899266435f)
+
+static __host__ __device__ __forceinline__ size_t g4r_align(size_t x, size_t a = 256) {
+    return (x + a - 1) / a * a;
+}
+
+// ---- scratch layouts (host+device agree through these) --------------------------------
+struct GeomLayout {      // per-Gaussian state, saved for backward
+    size_t rec, clamped, total;
+    __host__ __device__ explicit GeomLayout(int P) {
+        size_t o = 0;
+        rec = o;      o = g4r_align(o + (size_t)P * 48);
+        clamped = o;  o = g4r_align(o + (size_t)P);
+        total = o + 256;
+    }
+};
+struct ImageLayout {     // per-pixel + per-tile state, saved for backward
+    size_t header, counts, cursors, ranges, final_T, n_contrib, total;
+    int tiles_x, tiles_y, tiles;
+    __host__ __device__ ImageLayout(int W, int H) {
+        tiles_x = (W + G4R_TILE - 1) / G4R_TILE;
+        tiles_y = (H + G4R_TILE - 1) / G4R_TILE;
+        tiles = tiles_x * tiles_y;
+        size_t o = 0;
+        header = o;    o = g4r_align(o + G4R_HEADER_WORDS * 4);
+        counts = o;    o = g4r_align(o + (size_t)tiles * 4);
+        cursors = o;   o = g4r_align(o + (size_t)tiles * 4);
+        ranges = o;    o = g4r_align(o + (size_t)tiles * 8);
+        final_T = o;   o = g4r_align(o + (size_t)W * H * 4);
+        n_contrib = o; o = g4r_align(o + (size_t)W * H * 4);
+        total = o + 256;
+    }
+};
+struct BinLayout {       // per-instance state; point_list is saved for backward
+    size_t point_list, pairs, pairs_alt, total;
+    __host__ __device__ explicit BinLayout(int64_t cap) {
+        size_t c = (size_t)(cap < 1 ? 1 : cap);
+        size_t o = 0;
+        point_list = o; o = g4r_align(o + c * 4);
+        pairs = o;      o = g4r_align(o + c * 8);
+        pairs_alt = o;  o = g4r_align(o + c * 8);
+        total = o + 256;
+    }
+};
+// backward accumulators: 12 floats per Gaussian
+//   [0]=dL/dmean2D.x [1]=dL/dmean2D.y [2]=dL/dconic.x [3]=dL/dconic.y [4]=dL/dconic.w
+//   [5]=dL/dopacity  [6]=dL/dcolor.r  [7]=dL/dcolor.g  [8]=dL/dcolor.b [9]=dL/ddepth
+#define G4R_ACC_STRIDE 12
+
+// ---- small device helpers ---------------------------------------------------------------
+// float -> int32 with the semantics of PTX cvt.rzi.s32.f32 (truncate, saturate, NaN -> 0),
+// which is what a C cast compiles to on the GPU (and what the oracle emulates on the CPU).
+static __device__ __forceinline__ int f2i_rz(float v) { return __float2int_rz(v); }
+
+struct TileRect { uint32_t x0, y0, x1, y1; };
+
+// Tile rectangle of a splat, bit-exact to getRect (DGR/cuda_rasterizer/auxiliary.h:46-56):
+// all arithmetic in float, one rounding per operation, in this order.
+static __device__ __forceinline__ TileRect tile_rect(float px, float py, int radius, uint32_t gx, uint32_t gy) {
+    const float rf = (float)radius;
+    TileRect r;
+    r.x0 = min(gx, (uint32_t)max(0, f2i_rz(__fmul_rn(__fsub_rn(px, rf), 0.0625f))));
+    r.y0 = min(gy, (uint32_t)max(0, f2i_rz(__fmul_rn(__fsub_rn(py, rf), 0.0625f))));
+    r.x1 = min(gx, (uint32_t)max(0, f2i_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(px, rf), 16.0f), -1.0f), 0.0625f))));
+    r.y1 = min(gy, (uint32_t)max(0, f2i_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(py, rf), 16.0f), -1.0f), 0.0625f))));
+    return r;
+}
+
+// 128-bit read-only loads (LDG.E.128.CONSTANT) for the record gathers.
+static __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Host-side launch check.
+int g4r_set_error(int code, const char* fmt, ...);
+#define G4R_CUDA_OK(expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return g4r_set_error(G4R_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+#define G4R_LAUNCH_OK(name)                                                               \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess)                                                           \
+            return g4r_set_error(G4R_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- kernel launchers (one translation unit each) ----------------------------------------
+int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* img, int32_t* radii, int32_t* n_touched,
+                   cudaStream_t s);
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
+int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s);
+int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
+                        int64_t capacity, cudaStream_t s);
+int launch_composite_forward(const G4RFrame& f, int P, const void* geom, void* img, const void* binning, int64_t capacity,
+                             const G4RForwardOut& out, cudaStream_t s);
+int launch_composite_backward(const G4RFrame& f, int P, const void* geom, const void* img, const void* binning,
+                              const float* dL_dcolor, const float* dL_ddepth, float* acc, cudaStream_t s);
+int launch_gaussian_backward(const G4RFrame& f, const G4RGaussians& g, const int32_t* radii, const void* geom,
+                             const float* acc, const G4RBackwardIO& io, cudaStream_t s);

@@ -1,0 +1,462 @@
+"""B200-native drop-in for the ``diff_gaussian_rasterization`` extension of yanyan-li/4DGS-SLAM.
+
+Python surface mirrors the reference package line for line in *behaviour*
+(``/root/reference/submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py``):
+
+* ``GaussianRasterizationSettings``  -- reference ``__init__.py:173-186`` (same 13 fields, same order)
+* ``GaussianRasterizer``             -- reference ``__init__.py:188-244`` (``forward`` / ``markVisible``)
+* ``rasterize_gaussians``            -- reference ``__init__.py:21-46``
+* ``_RasterizeGaussians``            -- reference ``__init__.py:48-171`` (autograd op, same input / gradient order)
+
+so ``gaussian_splatting/gaussian_renderer/__init__.py:15-18,87-106,180-214`` (``render`` / ``render_flow``),
+``utils/slam_frontend.py`` and ``utils/slam_backend.py`` run unchanged on top of it.
+
+The native side is NOT a torch extension: it is a plain C-ABI shared library (``libg4r.so``, built from
+``4dgs-slam_b200/csrc/*.cu`` for sm_100a, declared in ``include/g4r.h``) loaded with ctypes.  torch only
+provides device memory and the current stream.  There is no CPU or PyTorch fallback: if the library is
+missing, importing this package raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+__all__ = [
+    "GaussianRasterizationSettings",
+    "GaussianRasterizer",
+    "rasterize_gaussians",
+    "rasterize_gaussians_with_state",
+]
+
+# ----------------------------------------------------------------------------------------------
+# native library
+# ----------------------------------------------------------------------------------------------
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libg4r.so")
+
+
+class _Frame(ctypes.Structure):
+    _fields_ = [
+        ("width", ctypes.c_int32), ("height", ctypes.c_int32),
+        ("tan_fovx", ctypes.c_float), ("tan_fovy", ctypes.c_float), ("scale_modifier", ctypes.c_float),
+        ("sh_degree", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32), ("prefiltered", ctypes.c_int32),
+        ("bg", ctypes.c_void_p), ("viewmatrix", ctypes.c_void_p), ("projmatrix", ctypes.c_void_p),
+        ("projmatrix_raw", ctypes.c_void_p), ("campos", ctypes.c_void_p),
+    ]
+
+
+class _Gaussians(ctypes.Structure):
+    _fields_ = [
+        ("P", ctypes.c_int32),
+        ("means3D", ctypes.c_void_p), ("opacities", ctypes.c_void_p), ("shs", ctypes.c_void_p),
+        ("colors_precomp", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p),
+        ("cov3D_precomp", ctypes.c_void_p),
+    ]
+
+
+class _ForwardOut(ctypes.Structure):
+    _fields_ = [
+        ("color", ctypes.c_void_p), ("depth", ctypes.c_void_p), ("opacity", ctypes.c_void_p),
+        ("radii", ctypes.c_void_p), ("n_touched", ctypes.c_void_p),
+    ]
+
+
+class _BackwardIO(ctypes.Structure):
+    _fields_ = [
+        ("dL_dcolor", ctypes.c_void_p), ("dL_ddepth", ctypes.c_void_p),
+        ("dL_dmeans3D", ctypes.c_void_p), ("dL_dmeans2D", ctypes.c_void_p), ("dL_dopacity", ctypes.c_void_p),
+        ("dL_dshs", ctypes.c_void_p), ("dL_dcolors_precomp", ctypes.c_void_p), ("dL_dscales", ctypes.c_void_p),
+        ("dL_drotations", ctypes.c_void_p), ("dL_dcov3D", ctypes.c_void_p), ("dL_dtau", ctypes.c_void_p),
+    ]
+
+
+class _Layout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_size_t) for n in (
+        "geom_rec", "geom_clamped", "img_final_T", "img_n_contrib", "img_ranges", "img_counts", "img_header",
+        "bin_point_list", "bin_pairs")]
+
+
+def _load_library() -> ctypes.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"diff_gaussian_rasterization (B200-native): {_LIB_PATH} is missing. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` from the repository root "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU / PyTorch fallback."
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+    lib.g4r_last_error.restype = ctypes.c_char_p
+    lib.g4r_last_error.argtypes = []
+    lib.g4r_version.restype = ctypes.c_int
+    lib.g4r_version.argtypes = []
+    lib.g4r_context_create.restype = ctypes.c_int
+    lib.g4r_context_create.argtypes = [ctypes.POINTER(vp)]
+    lib.g4r_context_destroy.restype = None
+    lib.g4r_context_destroy.argtypes = [vp]
+    lib.g4r_geom_bytes.restype = sz
+    lib.g4r_geom_bytes.argtypes = [i32]
+    lib.g4r_image_bytes.restype = sz
+    lib.g4r_image_bytes.argtypes = [i32, i32]
+    lib.g4r_binning_bytes.restype = sz
+    lib.g4r_binning_bytes.argtypes = [i64]
+    lib.g4r_backward_scratch_bytes.restype = sz
+    lib.g4r_backward_scratch_bytes.argtypes = [i32]
+    lib.g4r_forward_project.restype = ctypes.c_int
+    lib.g4r_forward_project.argtypes = [vp, ctypes.POINTER(_Frame), ctypes.POINTER(_Gaussians), vp, vp, vp, vp, vp]
+    lib.g4r_forward_render.restype = ctypes.c_int
+    lib.g4r_forward_render.argtypes = [vp, ctypes.POINTER(_Frame), ctypes.POINTER(_Gaussians), vp, vp, vp, i64,
+                                       ctypes.POINTER(_ForwardOut), vp]
+    lib.g4r_wait_num_rendered.restype = i64
+    lib.g4r_wait_num_rendered.argtypes = [vp]
+    lib.g4r_backward.restype = ctypes.c_int
+    lib.g4r_backward.argtypes = [ctypes.POINTER(_Frame), ctypes.POINTER(_Gaussians), vp, vp, vp, vp, vp,
+                                 ctypes.POINTER(_BackwardIO), vp]
+    lib.g4r_mark_visible.restype = ctypes.c_int
+    lib.g4r_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.g4r_layout.restype = ctypes.c_int
+    lib.g4r_layout.argtypes = [i32, i32, i32, i64, ctypes.POINTER(_Layout)]
+    return lib
+
+
+_lib = _load_library()
+LIBRARY_PATH = _LIB_PATH
+
+
+def _check(rc: int) -> None:
+    if rc < 0:
+        raise RuntimeError(_lib.g4r_last_error().decode("utf-8", "replace"))
+
+
+_tls = threading.local()
+
+
+def _context(device: torch.device) -> int:
+    """One native context (pinned int + event) per host thread and device."""
+    table = getattr(_tls, "ctx", None)
+    if table is None:
+        table = _tls.ctx = {}
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    h = table.get(idx)
+    if h is None:
+        out = ctypes.c_void_p()
+        _check(_lib.g4r_context_create(ctypes.byref(out)))
+        h = table[idx] = out.value
+    return h
+
+
+# instance-capacity hint per device: high-water mark of num_rendered with slow decay
+_cap_hint: dict = {}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _dev_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    if t.dtype != torch.float32 or t.device != device:
+        t = t.to(device=device, dtype=torch.float32)
+    return t.contiguous()
+
+
+def _make_frame(rs: "GaussianRasterizationSettings", device: torch.device, sh_coeffs: int, keep: list) -> _Frame:
+    def mat(t):
+        t = _dev_f32(t, device)
+        keep.append(t)
+        return t.data_ptr()
+
+    f = _Frame()
+    f.width, f.height = int(rs.image_width), int(rs.image_height)
+    f.tan_fovx, f.tan_fovy = float(rs.tanfovx), float(rs.tanfovy)
+    f.scale_modifier = float(rs.scale_modifier)
+    f.sh_degree, f.sh_coeffs = int(rs.sh_degree), int(sh_coeffs)
+    f.prefiltered = int(bool(rs.prefiltered))
+    f.bg, f.viewmatrix, f.projmatrix = mat(rs.bg), mat(rs.viewmatrix), mat(rs.projmatrix)
+    f.projmatrix_raw, f.campos = mat(rs.projmatrix_raw), mat(rs.campos)
+    return f
+
+
+def _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp) -> _Gaussians:
+    g = _Gaussians()
+    g.P = P
+    g.means3D, g.opacities = _ptr(means3D), _ptr(opacities)
+    g.shs, g.colors_precomp = _ptr(sh), _ptr(colors_precomp)
+    g.scales, g.rotations, g.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp)
+    return g
+
+
+def _layout(P: int, W: int, H: int, cap: int) -> _Layout:
+    lay = _Layout()
+    _check(_lib.g4r_layout(P, W, H, cap, ctypes.byref(lay)))
+    return lay
+
+
+# ----------------------------------------------------------------------------------------------
+# forward / backward drivers
+# ----------------------------------------------------------------------------------------------
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:58-60
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (B200-native): means3D must be a CUDA tensor; there is no CPU path")
+    device = means3D.device
+    P = int(means3D.size(0))
+    H, W = int(rs.image_height), int(rs.image_width)
+
+    means3D = _dev_f32(means3D, device)
+    opacities = _dev_f32(opacities, device)
+    sh = _dev_f32(sh, device) if sh.numel() else sh
+    colors_precomp = _dev_f32(colors_precomp, device) if colors_precomp.numel() else colors_precomp
+    scales = _dev_f32(scales, device) if scales.numel() else scales
+    rotations = _dev_f32(rotations, device) if rotations.numel() else rotations
+    cov3Ds_precomp = _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp
+    M = int(sh.size(1)) if sh.numel() else 0                                    # rasterize_points.cu:87-91
+
+    f32 = dict(dtype=torch.float32, device=device)
+    i32 = dict(dtype=torch.int32, device=device)
+    u8 = dict(dtype=torch.uint8, device=device)
+    if P == 0:
+        # rasterize_points.cu:69-73,85: zero images, no kernels
+        z = torch.zeros
+        state = dict(P=0, N=0, geom=torch.empty(0, **u8), img=torch.empty(0, **u8), binning=torch.empty(0, **u8), capacity=0)
+        return z((3, H, W), **f32), torch.zeros((0,), **i32), z((1, H, W), **f32), z((1, H, W), **f32), torch.zeros((0,), **i32), state
+
+    color = torch.empty((3, H, W), **f32)
+    depth = torch.empty((1, H, W), **f32)
+    opacity = torch.empty((1, H, W), **f32)
+    radii = torch.empty((P,), **i32)
+    n_touched = torch.empty((P,), **i32)
+    geom = torch.empty((_lib.g4r_geom_bytes(P),), **u8)
+    img = torch.empty((_lib.g4r_image_bytes(W, H),), **u8)
+
+    keep: list = []
+    with torch.cuda.device(device):
+        ctx = _context(device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        frame = _make_frame(rs, device, M, keep)
+        g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+        out = _ForwardOut(color.data_ptr(), depth.data_ptr(), opacity.data_ptr(), radii.data_ptr(), n_touched.data_ptr())
+
+        _check(_lib.g4r_forward_project(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
+                                        radii.data_ptr(), n_touched.data_ptr(), stream))
+        # Phase 2 is enqueued with a speculative capacity; N is checked only after everything is in the
+        # stream, so the device never waits for the host (the reference blocks on a cudaMemcpy instead,
+        # rasterizer_impl.cu:284).
+        key = (device.index, W, H)
+        hint = _cap_hint.get(key, 0)
+        cap = int(max(hint, 4 * P) * 1.25) + 4096 if hint == 0 else int(hint * 1.25) + 4096
+        binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
+        _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
+                                       binning.data_ptr(), cap, ctypes.byref(out), stream))
+        N = int(_lib.g4r_wait_num_rendered(ctx))
+        if N < 0:
+            _check(N)
+        if N > cap:
+            cap = N
+            binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
+            _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
+                                           binning.data_ptr(), cap, ctypes.byref(out), stream))
+        _cap_hint[key] = max(N, int(hint * 0.95))
+    state = dict(P=P, N=N, geom=geom, img=img, binning=binning, capacity=cap)
+    return color, radii, depth, opacity, n_touched, state
+
+
+def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii, geom, img, binning,
+                   opacities_shape, grad_out_color, grad_out_depth):
+    device = means3D.device
+    H, W = int(rs.image_height), int(rs.image_width)
+    f32 = dict(dtype=torch.float32, device=device)
+    M = int(sh.size(1)) if sh.numel() else 0
+    tau = torch.empty((8,), **f32)
+    grad_means3D = torch.empty((P, 3), **f32)
+    grad_means2D = torch.empty((P, 3), **f32)
+    grad_opacities = torch.empty(opacities_shape, **f32)
+    grad_sh = torch.empty((P, M, 3), **f32) if sh.numel() else None
+    grad_colors = torch.empty((P, 3), **f32) if colors_precomp.numel() else None
+    grad_scales = torch.empty((P, 3), **f32) if scales.numel() else None
+    grad_rot = torch.empty((P, 4), **f32) if rotations.numel() else None
+    grad_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp.numel() else None
+    if P == 0:
+        tau.zero_()
+        return grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau
+
+    grad_out_color = _dev_f32(grad_out_color, device)
+    grad_out_depth = _dev_f32(grad_out_depth, device)
+    scratch = torch.empty((_lib.g4r_backward_scratch_bytes(P),), dtype=torch.uint8, device=device)
+    keep: list = []
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        frame = _make_frame(rs, device, M, keep)
+        g = _make_gaussians(P, means3D, None, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+        g.opacities = means3D.data_ptr()   # opacities are not read in backward (they live in the splat records)
+        io = _BackwardIO(grad_out_color.data_ptr(), grad_out_depth.data_ptr(), grad_means3D.data_ptr(), grad_means2D.data_ptr(),
+                         grad_opacities.data_ptr(), _ptr(grad_sh), _ptr(grad_colors), _ptr(grad_scales), _ptr(grad_rot),
+                         _ptr(grad_cov), tau.data_ptr())
+        _check(_lib.g4r_backward(ctypes.byref(frame), ctypes.byref(g), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
+                                 binning.data_ptr(), scratch.data_ptr(), ctypes.byref(io), stream))
+    return grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau
+
+
+# ----------------------------------------------------------------------------------------------
+# public surface (same names / order as the reference package)
+# ----------------------------------------------------------------------------------------------
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                     theta, rho, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho,
+                raster_settings):
+        color, radii, depth, opacity, n_touched, state = _forward_impl(
+            means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = state["N"]
+        ctx.P = state["P"]
+        ctx.opacities_shape = tuple(opacities.shape)
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
+                              state["geom"], state["binning"], state["img"])
+        ctx.mark_non_differentiable(radii, n_touched)
+        return color, radii, depth, opacity, n_touched
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_radii, grad_out_depth, grad_out_opacity, grad_n_touched):
+        # like the reference, grad_out_opacity / radii / n_touched are dropped (reference __init__.py:108-130)
+        rs = ctx.raster_settings
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img = ctx.saved_tensors
+        device = means3D.device
+        means3D_c = _dev_f32(means3D, device)
+        (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau) = _backward_impl(
+            rs, ctx.P, means3D_c,
+            _dev_f32(sh, device) if sh.numel() else sh,
+            _dev_f32(colors_precomp, device) if colors_precomp.numel() else colors_precomp,
+            _dev_f32(scales, device) if scales.numel() else scales,
+            _dev_f32(rotations, device) if rotations.numel() else rotations,
+            _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp,
+            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth)
+        grad_rho = tau[:3].view(1, -1)
+        grad_theta = tau[3:6].view(1, -1)
+        needs = ctx.needs_input_grad
+        return (
+            grad_means3D,
+            grad_means2D,
+            grad_sh,
+            grad_colors,
+            grad_opacities,
+            grad_scales,
+            grad_rot,
+            grad_cov,
+            grad_theta if needs[8] else None,
+            grad_rho if needs[9] else None,
+            None,
+        )
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    projmatrix_raw: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _empty() -> torch.Tensor:
+    return torch.Tensor([])
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Boolean mask of points in front of the near plane (view-space z > 0.2)."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            if not positions.is_cuda:
+                raise RuntimeError("diff_gaussian_rasterization (B200-native): positions must be a CUDA tensor")
+            device = positions.device
+            pos = _dev_f32(positions, device)
+            P = int(pos.size(0))
+            present = torch.zeros((P,), dtype=torch.bool, device=device)
+            if P:
+                view = _dev_f32(rs.viewmatrix, device)
+                proj = _dev_f32(rs.projmatrix, device)
+                with torch.cuda.device(device):
+                    _check(_lib.g4r_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(), present.data_ptr(),
+                                                 torch.cuda.current_stream(device).cuda_stream))
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, theta=None, rho=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+            (scales is not None or rotations is not None) and cov3D_precomp is not None
+        ):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+
+        if shs is None:
+            shs = _empty()
+        if colors_precomp is None:
+            colors_precomp = _empty()
+        if scales is None:
+            scales = _empty()
+        if rotations is None:
+            rotations = _empty()
+        if cov3D_precomp is None:
+            cov3D_precomp = _empty()
+        if theta is None:
+            theta = _empty()
+        if rho is None:
+            rho = _empty()
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   theta, rho, raster_settings)
+
+
+# ----------------------------------------------------------------------------------------------
+# inspection hook used by the parity tests (not part of the reference surface)
+# ----------------------------------------------------------------------------------------------
+def rasterize_gaussians_with_state(raster_settings, means3D, opacities, shs=None, colors_precomp=None, scales=None,
+                                   rotations=None, cov3D_precomp=None):
+    """Forward only (no autograd); returns the 5 outputs plus the saved integer state:
+    ``num_rendered``, ``point_list`` (N,), ``ranges`` (tiles,2), ``n_contrib`` (H,W), ``final_T`` (H,W)."""
+    e = _empty()
+    with torch.no_grad():
+        color, radii, depth, opacity, n_touched, st = _forward_impl(
+            means3D, shs if shs is not None else e, colors_precomp if colors_precomp is not None else e, opacities,
+            scales if scales is not None else e, rotations if rotations is not None else e,
+            cov3D_precomp if cov3D_precomp is not None else e, raster_settings)
+    H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+    P, N = st["P"], st["N"]
+    info = dict(num_rendered=N)
+    if P:
+        lay = _layout(P, W, H, st["capacity"])
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        img, binning, geom = st["img"], st["binning"], st["geom"]
+        info["point_list"] = binning[lay.bin_point_list: lay.bin_point_list + 4 * N].view(torch.int32).clone()
+        info["ranges"] = img[lay.img_ranges: lay.img_ranges + 8 * tiles].view(torch.int32).view(tiles, 2).clone()
+        info["n_contrib"] = img[lay.img_n_contrib: lay.img_n_contrib + 4 * H * W].view(torch.int32).view(H, W).clone()
+        info["final_T"] = img[lay.img_final_T: lay.img_final_T + 4 * H * W].view(torch.float32).view(H, W).clone()
+        info["rec"] = geom[lay.geom_rec: lay.geom_rec + 48 * P].view(torch.float32).view(P, 12).clone()
+    return (color, radii, depth, opacity, n_touched), info

@@ -1,0 +1,174 @@
+/*
+ * g4r.h -- C ABI of the B200-native differentiable Gaussian rasterizer ("g4r").
+ *
+ * This is the drop-in boundary for the ONE hot path of yanyan-li/4DGS-SLAM: the
+ * diff_gaussian_rasterization extension.  Every entry point below replaces a
+ * function of the reference's native layer (citations relative to
+ * /root/reference/submodules/diff-gaussian-rasterization/, "DGR/"):
+ *
+ *   g4r_forward_project + g4r_forward_render
+ *        == CudaRasterizer::Rasterizer::forward      DGR/cuda_rasterizer/rasterizer_impl.cu:198-344
+ *           (called from RasterizeGaussiansCUDA        DGR/rasterize_points.cu:35-122)
+ *   g4r_backward
+ *        == CudaRasterizer::Rasterizer::backward     DGR/cuda_rasterizer/rasterizer_impl.cu:348-455
+ *           (called from RasterizeGaussiansBackwardCUDA DGR/rasterize_points.cu:124-211)
+ *           plus the (P,6)->(6) pose-gradient sum of  DGR/diff_gaussian_rasterization/__init__.py:152-154
+ *   g4r_mark_visible
+ *        == CudaRasterizer::Rasterizer::markVisible  DGR/cuda_rasterizer/rasterizer_impl.cu:141-153
+ *   g4r_geom_bytes / g4r_image_bytes / g4r_binning_bytes / g4r_backward_scratch_bytes
+ *        == required<GeometryState|ImageState|BinningState>() DGR/cuda_rasterizer/rasterizer_impl.h:64-72
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*. No torch
+ *     types, no C++ exceptions cross this boundary.
+ *   - every function returns 0 on success or a negative G4R_E* code; the text of
+ *     the last error on the calling thread is available from g4r_last_error().
+ *   - all buffers are owned by the caller (the Python side hands in torch tensors
+ *     so autograd keeps them alive until backward, like the reference's
+ *     geomBuffer/binningBuffer/imgBuffer).  Optional inputs are NULL, mirroring
+ *     the reference's empty-tensor sentinels (DGR/rasterize_points.cu:85-117).
+ *   - all work is enqueued on `stream`; nothing here synchronises the device
+ *     except g4r_wait_num_rendered(), which waits on one event.
+ *   - float32 everywhere; matrices are 16 floats in the reference's layout
+ *     (column-major world->view / full projection).
+ */
+#ifndef G4R_H_INCLUDED
+#define G4R_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G4R_OK            0
+#define G4R_EINVAL       -1   /* bad argument (NULL where required, negative size, ...) */
+#define G4R_ECUDA        -2   /* a CUDA runtime call or kernel launch failed            */
+#define G4R_EOVERFLOW    -3   /* binning capacity too small (informational)              */
+
+#define G4R_TILE          16  /* tile edge in pixels: BLOCK_X/BLOCK_Y of DGR/cuda_rasterizer/config.h:16-17 */
+#define G4R_CHANNELS      3   /* NUM_CHANNELS of DGR/cuda_rasterizer/config.h:15 */
+
+/* Per-frame camera + raster settings: the numeric fields of
+ * GaussianRasterizationSettings (DGR/diff_gaussian_rasterization/__init__.py:173-186).
+ * Pointers are DEVICE pointers, read by the kernels (never by the host). */
+typedef struct G4RFrame {
+    int32_t width;                /* image_width  */
+    int32_t height;               /* image_height */
+    float   tan_fovx;
+    float   tan_fovy;
+    float   scale_modifier;
+    int32_t sh_degree;            /* active degree D (0..3) */
+    int32_t sh_coeffs;            /* M = coefficients allocated per Gaussian (sh.size(1)); 0 when no SH */
+    int32_t prefiltered;          /* accepted for API parity; a culled point is simply skipped */
+    const float* bg;              /* [3]  */
+    const float* viewmatrix;      /* [16] */
+    const float* projmatrix;      /* [16] */
+    const float* projmatrix_raw;  /* [16] backward only (pose Jacobian); may be NULL in forward */
+    const float* campos;          /* [3]  */
+} G4RFrame;
+
+/* Per-Gaussian inputs (all DEVICE pointers, contiguous, read-only). */
+typedef struct G4RGaussians {
+    int32_t P;                    /* number of Gaussians */
+    const float* means3D;         /* [P,3] */
+    const float* opacities;       /* [P]   (post-sigmoid) */
+    const float* shs;             /* [P,M,3] or NULL */
+    const float* colors_precomp;  /* [P,3]   or NULL  (exactly one of shs/colors_precomp) */
+    const float* scales;          /* [P,3] (post-exp)  or NULL */
+    const float* rotations;       /* [P,4] (w,x,y,z)   or NULL */
+    const float* cov3D_precomp;   /* [P,6] or NULL  (exactly one of scales+rotations / cov3D_precomp) */
+} G4RGaussians;
+
+/* Forward outputs (DEVICE pointers, written in full; no pre-zeroing needed). */
+typedef struct G4RForwardOut {
+    float*   color;               /* [3,H,W] */
+    float*   depth;               /* [1,H,W] */
+    float*   opacity;             /* [1,H,W] */
+    int32_t* radii;               /* [P]     */
+    int32_t* n_touched;           /* [P]     */
+} G4RForwardOut;
+
+/* Incoming image gradients + outgoing per-Gaussian gradients (DEVICE pointers).
+ * Every output is written in full (zeros for invisible Gaussians), so the caller
+ * may hand in uninitialised memory.  Outputs whose input was absent may be NULL. */
+typedef struct G4RBackwardIO {
+    const float* dL_dcolor;       /* [3,H,W] */
+    const float* dL_ddepth;       /* [1,H,W] */
+    float* dL_dmeans3D;           /* [P,3]   */
+    float* dL_dmeans2D;           /* [P,3]   (x,y screen-space NDC-scaled; z = 0) */
+    float* dL_dopacity;           /* [P]     */
+    float* dL_dshs;               /* [P,M,3] or NULL */
+    float* dL_dcolors_precomp;    /* [P,3]   or NULL */
+    float* dL_dscales;            /* [P,3]   or NULL */
+    float* dL_drotations;         /* [P,4]   or NULL */
+    float* dL_dcov3D;             /* [P,6]   or NULL (only when cov3D_precomp was given) */
+    float* dL_dtau;               /* [8]: [0:3] = grad_rho, [3:6] = grad_theta, [6:8] padding */
+} G4RBackwardIO;
+
+typedef struct G4RContext G4RContext;   /* owns one pinned int + one event; one per host thread/device */
+
+/* ---- library / context ------------------------------------------------------------ */
+const char* g4r_last_error(void);
+int  g4r_version(void);                               /* ABI version, currently 1 */
+int  g4r_context_create(G4RContext** out);
+void g4r_context_destroy(G4RContext* ctx);
+
+/* ---- scratch sizing (bytes) --------------------------------------------------------- */
+size_t g4r_geom_bytes(int32_t P);                     /* per-Gaussian splat records, saved for backward */
+size_t g4r_image_bytes(int32_t width, int32_t height);/* per-pixel final_T/n_contrib + per-tile ranges  */
+size_t g4r_binning_bytes(int64_t capacity);           /* room for `capacity` (tile,Gaussian) instances  */
+size_t g4r_backward_scratch_bytes(int32_t P);         /* per-Gaussian gradient accumulators (not saved) */
+
+/* ---- forward, phase 1: projection + tile histogram + tile offsets --------------------
+ * Enqueues: per-Gaussian projection (writes radii, zeroes n_touched, fills geom), per-tile instance
+ * counts and their exclusive scan (writes ranges into img), then an async copy of the
+ * instance total N into the context's pinned int and an event record.
+ * Never blocks. */
+int g4r_forward_project(G4RContext* ctx, const G4RFrame* frame, const G4RGaussians* g,
+                        void* geom, void* img, int32_t* radii, int32_t* n_touched, void* stream);
+
+/* ---- forward, phase 2: instance scatter + per-tile depth sort + composite -------------
+ * `capacity` = number of instances `binning` has room for.  If the device-side N
+ * turns out larger, every phase-2 kernel exits without touching memory and the
+ * caller must call again with a larger buffer (see g4r_wait_num_rendered).
+ * Never blocks. */
+int g4r_forward_render(G4RContext* ctx, const G4RFrame* frame, const G4RGaussians* g,
+                       void* geom, void* img, void* binning, int64_t capacity,
+                       const G4RForwardOut* out, void* stream);
+
+/* Waits for the event recorded by g4r_forward_project and returns N (>= 0), the
+ * reference's `num_rendered` (DGR/cuda_rasterizer/rasterizer_impl.cu:283-284), or a
+ * negative error code.  By the time phase 2 has been enqueued the event has normally
+ * already fired, so the GPU is never idle waiting for the host. */
+int64_t g4r_wait_num_rendered(G4RContext* ctx);
+
+/* ---- backward ------------------------------------------------------------------------ */
+int g4r_backward(const G4RFrame* frame, const G4RGaussians* g,
+                 const int32_t* radii, const void* geom, const void* img, const void* binning,
+                 void* scratch, const G4RBackwardIO* io, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------- */
+int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Test / inspection hooks: byte offsets of the saved state inside the caller's buffers
+ * (the parity tests read radii, point_list, ranges, n_contrib through these). */
+typedef struct G4RLayout {
+    size_t geom_rec;        /* float4[3*P]: {mx,my,conic.x,conic.y} {conic.z,opacity,depth,r} {g,b,cull_hx,cull_hy} */
+    size_t geom_clamped;    /* uint8[P]: bit c set when SH colour channel c was clamped at 0 */
+    size_t img_final_T;     /* float[H*W]    */
+    size_t img_n_contrib;   /* uint32[H*W]   */
+    size_t img_ranges;      /* uint2[tiles]  */
+    size_t img_counts;      /* uint32[tiles] */
+    size_t img_header;      /* uint32[8]: [0] = N */
+    size_t bin_point_list;  /* uint32[capacity] sorted Gaussian ids == reference point_list */
+    size_t bin_pairs;       /* uint2[capacity]  unsorted (depth bits, id) */
+} G4RLayout;
+int g4r_layout(int32_t P, int32_t width, int32_t height, int64_t capacity, G4RLayout* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G4R_H_INCLUDED */

@@ -1,0 +1,173 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/g4r_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg may import this module; the
+product package (``4dgs-slam_b200/diff_gaussian_rasterization``) never does.
+
+``Oracle("f32")`` follows the reference's float32 arithmetic (bit-faithful on radii / tile rectangles / depth
+keys); ``Oracle("f64")`` is the same algorithm in double precision, used for finite-difference checks.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+
+def build(force: bool = False) -> None:
+    """Compile both oracle libraries with the committed Makefile (gcc, -ffp-contract=off)."""
+    need = force or not all(os.path.exists(os.path.join(_BUILD, f"libg4r_oracle_{p}.so")) for p in ("f32", "f64"))
+    src = os.path.join(_HERE, "g4r_oracle.c")
+    if not need:
+        need = any(os.path.getmtime(os.path.join(_BUILD, f"libg4r_oracle_{p}.so")) < os.path.getmtime(src) for p in ("f32", "f64"))
+    if need:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
+
+
+def _scene_struct(real):
+    class OracleScene(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_int32) for n in ("P", "D", "M", "W", "H")] + \
+                   [(n, real) for n in ("tan_fovx", "tan_fovy", "scale_modifier")] + \
+                   [(n, ctypes.c_void_p) for n in ("bg", "viewmatrix", "projmatrix", "projmatrix_raw", "campos", "means3D",
+                                                   "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp")]
+    return OracleScene
+
+
+class _Geom(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "radii", "tiles_touched")]
+
+
+class _Grads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("dL_dmeans3D", "dL_dmeans2D", "dL_dopacity", "dL_dcolors", "dL_dcov3D", "dL_dshs",
+                                               "dL_dscales", "dL_drots", "dL_dtau_rows", "dL_dtau")]
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Oracle:
+    def __init__(self, precision: str = "f32"):
+        assert precision in ("f32", "f64")
+        build()
+        self.precision = precision
+        self.dtype = np.float32 if precision == "f32" else np.float64
+        self.real = ctypes.c_float if precision == "f32" else ctypes.c_double
+        self.lib = ctypes.CDLL(os.path.join(_BUILD, f"libg4r_oracle_{precision}.so"))
+        self.Scene = _scene_struct(self.real)
+        s = "_" + precision
+        self._project = getattr(self.lib, "oracle_project" + s)
+        self._bin = getattr(self.lib, "oracle_bin" + s)
+        self._bin.restype = ctypes.c_int64
+        self._free = getattr(self.lib, "oracle_free" + s)
+        self._free.argtypes = [ctypes.c_void_p]
+        self._composite = getattr(self.lib, "oracle_composite" + s)
+        self._composite_bw = getattr(self.lib, "oracle_composite_bw" + s)
+        self._gaussian_bw = getattr(self.lib, "oracle_gaussian_bw" + s)
+        self._mark_visible = getattr(self.lib, "oracle_mark_visible" + s)
+
+    # ------------------------------------------------------------------------------------------
+    def _arr(self, a, shape=None):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(np.asarray(a, dtype=self.dtype))
+        if shape is not None:
+            a = a.reshape(shape)
+        return a
+
+    def _pack(self, sc: dict):
+        """sc: dict with the keys of tools.scenes.Scene (numpy or torch CPU tensors)."""
+        def get(k):
+            v = sc.get(k)
+            if v is None:
+                return None
+            if hasattr(v, "detach"):
+                v = v.detach().cpu().numpy()
+            return self._arr(v)
+
+        keep = {k: get(k) for k in ("bg", "viewmatrix", "projmatrix", "projmatrix_raw", "campos", "means3D", "opacities", "shs",
+                                    "colors_precomp", "scales", "rotations", "cov3D_precomp")}
+        P = int(keep["means3D"].shape[0])
+        M = int(keep["shs"].shape[1]) if keep["shs"] is not None else 0
+        S = self.Scene()
+        S.P, S.D, S.M, S.W, S.H = P, int(sc["sh_degree"]), M, int(sc["W"]), int(sc["H"])
+        # the reference receives tanfov / scale_modifier as C floats (pybind double -> float)
+        S.tan_fovx = float(np.float32(sc["tanfovx"])) if self.precision == "f32" else float(sc["tanfovx"])
+        S.tan_fovy = float(np.float32(sc["tanfovy"])) if self.precision == "f32" else float(sc["tanfovy"])
+        S.scale_modifier = float(sc.get("scale_modifier", 1.0))
+        for k, v in keep.items():
+            setattr(S, k, _p(v))
+        return S, keep, P, M
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, sc: dict) -> dict:
+        """Full forward: projection, binning, composite.  Returns outputs + every intermediate."""
+        S, keep, P, M = self._pack(sc)
+        W, H = S.W, S.H
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        dt = self.dtype
+        geom = dict(depths=np.zeros(P, dt), means2D=np.zeros((P, 2), dt), cov3D=np.zeros((P, 6), dt),
+                    conic_opacity=np.zeros((P, 4), dt), rgb=np.zeros((P, 3), dt), clamped=np.zeros((P, 3), np.uint8),
+                    radii=np.zeros(P, np.int32), tiles_touched=np.zeros(P, np.uint32))
+        G = _Geom(*[_p(geom[k]) for k in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "radii", "tiles_touched")])
+        self._project(ctypes.byref(S), ctypes.byref(G))
+        pl_ptr = ctypes.c_void_p()
+        ranges = np.zeros((tiles, 2), np.uint32)
+        N = int(self._bin(ctypes.byref(S), ctypes.byref(G), ctypes.byref(pl_ptr), ctypes.c_void_p(_p(ranges))))
+        point_list = np.ctypeslib.as_array(ctypes.cast(pl_ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(max(N, 1),))[:N].copy()
+        self._free(pl_ptr)
+        color = np.zeros((3, H, W), dt)
+        depth = np.zeros((1, H, W), dt)
+        opacity = np.zeros((1, H, W), dt)
+        final_T = np.zeros((H, W), dt)
+        n_contrib = np.zeros((H, W), np.uint32)
+        n_touched = np.zeros(P, np.int32)
+        pl = np.ascontiguousarray(point_list if N else np.zeros(1, np.uint32))
+        self._composite(ctypes.byref(S), ctypes.byref(G), ctypes.c_void_p(_p(pl)), ctypes.c_void_p(_p(ranges)),
+                        ctypes.c_void_p(_p(color)), ctypes.c_void_p(_p(depth)), ctypes.c_void_p(_p(opacity)),
+                        ctypes.c_void_p(_p(final_T)), ctypes.c_void_p(_p(n_contrib)), ctypes.c_void_p(_p(n_touched)))
+        out = dict(color=color, depth=depth, opacity=opacity, radii=geom["radii"], n_touched=n_touched, num_rendered=N,
+                   point_list=point_list, ranges=ranges, final_T=final_T, n_contrib=n_contrib, **{k: geom[k] for k in geom if k != "radii"})
+        out["_state"] = (S, keep, G, geom, pl, ranges, P, M)
+        return out
+
+    def backward(self, fwd: dict, grad_color, grad_depth) -> dict:
+        """Analytic backward of the reference, given a forward() result and upstream image gradients."""
+        S, keep, G, geom, pl, ranges, P, M = fwd["_state"]
+        dt = self.dtype
+        gc = self._arr(grad_color.detach().cpu().numpy() if hasattr(grad_color, "detach") else grad_color)
+        gd = self._arr(grad_depth.detach().cpu().numpy() if hasattr(grad_depth, "detach") else grad_depth)
+        acc = np.zeros((P, 10), np.float64)
+        self._composite_bw(ctypes.byref(S), ctypes.byref(G), ctypes.c_void_p(_p(pl)), ctypes.c_void_p(_p(ranges)),
+                           ctypes.c_void_p(_p(fwd["final_T"])), ctypes.c_void_p(_p(fwd["n_contrib"])), ctypes.c_void_p(_p(gc)),
+                           ctypes.c_void_p(_p(gd)), ctypes.c_void_p(_p(acc)))
+        has_sh, has_scale = keep["shs"] is not None, keep["scales"] is not None
+        g = dict(dL_dmeans3D=np.zeros((P, 3), dt), dL_dmeans2D=np.zeros((P, 3), dt), dL_dopacity=np.zeros(P, dt),
+                 dL_dcolors=np.zeros((P, 3), dt), dL_dcov3D=np.zeros((P, 6), dt),
+                 dL_dshs=np.zeros((P, M, 3), dt) if has_sh else None,
+                 dL_dscales=np.zeros((P, 3), dt) if has_scale else None, dL_drots=np.zeros((P, 4), dt) if has_scale else None,
+                 dL_dtau_rows=np.zeros((P, 6), dt), dL_dtau=np.zeros(6, dt))
+        GR = _Grads(*[_p(g[k]) for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dopacity", "dL_dcolors", "dL_dcov3D", "dL_dshs", "dL_dscales",
+                                         "dL_drots", "dL_dtau_rows", "dL_dtau")])
+        self._gaussian_bw(ctypes.byref(S), ctypes.byref(G), ctypes.c_void_p(_p(acc)), ctypes.byref(GR))
+        g["acc"] = acc
+        g["grad_rho"] = g["dL_dtau"][:3].copy()
+        g["grad_theta"] = g["dL_dtau"][3:].copy()
+        return g
+
+    def mark_visible(self, means3D, viewmatrix) -> np.ndarray:
+        m = self._arr(means3D)
+        v = self._arr(viewmatrix)
+        out = np.zeros(m.shape[0], np.uint8)
+        self._mark_visible(ctypes.c_int32(m.shape[0]), ctypes.c_void_p(_p(m)), ctypes.c_void_p(_p(v)), ctypes.c_void_p(_p(out)))
+        return out.astype(bool)
+
+
+def scene_dict(scene) -> dict:
+    """tools.scenes.Scene -> plain dict understood by Oracle.forward."""
+    return dict(scene.__dict__)
