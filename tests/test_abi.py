@@ -1,0 +1,78 @@
+"""The C-ABI library loads and exports every symbol include/g4r.h declares; sizing + argument validation work
+without a GPU (no kernel is launched here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "g4r.h")
+LIB = os.path.join(ROOT, "4dgs-slam_b200", "diff_gaussian_rasterization", "libg4r.so")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(g4r_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for s in ("g4r_forward_project", "g4r_forward_render", "g4r_wait_num_rendered", "g4r_backward", "g4r_mark_visible",
+              "g4r_geom_bytes", "g4r_image_bytes", "g4r_binning_bytes", "g4r_backward_scratch_bytes", "g4r_context_create",
+              "g4r_context_destroy", "g4r_last_error", "g4r_version", "g4r_layout"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(LIB)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_version_and_sizes():
+    lib = ctypes.CDLL(LIB)
+    assert lib.g4r_version() == 1
+    for f in (lib.g4r_geom_bytes, lib.g4r_binning_bytes, lib.g4r_backward_scratch_bytes, lib.g4r_image_bytes):
+        f.restype = ctypes.c_size_t
+    lib.g4r_geom_bytes.argtypes = [ctypes.c_int32]
+    lib.g4r_binning_bytes.argtypes = [ctypes.c_int64]
+    lib.g4r_backward_scratch_bytes.argtypes = [ctypes.c_int32]
+    lib.g4r_image_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    # 48-byte splat record + 1 clamp byte per Gaussian; 20 bytes per instance; 48 bytes of accumulators
+    assert lib.g4r_geom_bytes(1000) >= 49 * 1000
+    assert lib.g4r_geom_bytes(500_000) < 52 * 500_000
+    assert lib.g4r_binning_bytes(1_000_000) >= 20 * 1_000_000
+    assert lib.g4r_backward_scratch_bytes(1000) >= 48 * 1000
+    assert lib.g4r_image_bytes(640, 480) >= 8 * 640 * 480 + 16 * 1200
+    assert lib.g4r_geom_bytes(0) > 0 and lib.g4r_binning_bytes(0) > 0
+    prev = 0
+    for cap in (0, 1, 10, 1000, 10**6, 10**8):
+        b = lib.g4r_binning_bytes(cap)
+        assert b >= prev
+        prev = b
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    lib = ctypes.CDLL(LIB)
+    lib.g4r_last_error.restype = ctypes.c_char_p
+    rc = lib.g4r_forward_project(None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"context" in lib.g4r_last_error()
+    rc = lib.g4r_backward(None, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"frame" in lib.g4r_last_error()
+    lib.g4r_mark_visible.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 5
+    assert lib.g4r_mark_visible(-5, None, None, None, None, None) == -1
+    assert lib.g4r_mark_visible(0, None, None, None, None, None) == 0
+    lib.g4r_wait_num_rendered.restype = ctypes.c_int64
+    assert lib.g4r_wait_num_rendered(None) == -1
+
+
+def test_layout_offsets_are_aligned_and_ordered():
+    from diff_gaussian_rasterization import _Layout, _lib
+    lay = _Layout()
+    assert _lib.g4r_layout(1000, 640, 480, 5000, ctypes.byref(lay)) == 0
+    for name, _ in _Layout._fields_:
+        assert getattr(lay, name) % 16 == 0, name
+    assert lay.bin_point_list == 0 and lay.bin_pairs >= 4 * 5000
+    assert lay.img_n_contrib - lay.img_final_T >= 4 * 640 * 480

@@ -1,0 +1,79 @@
+"""Drop-in surface: same names, field order, argument checks and error messages as the reference package
+(DGR/diff_gaussian_rasterization/__init__.py:173-244); no CPU fallback."""
+import inspect
+
+import pytest
+import torch
+
+import diff_gaussian_rasterization as dgr
+
+
+def test_exports():
+    assert hasattr(dgr, "GaussianRasterizationSettings") and hasattr(dgr, "GaussianRasterizer")
+    assert hasattr(dgr, "rasterize_gaussians") and hasattr(dgr, "_RasterizeGaussians")
+
+
+def test_settings_fields_match_reference_order():
+    assert dgr.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "projmatrix_raw", "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_forward_signature_matches_reference():
+    sig = inspect.signature(dgr.GaussianRasterizer.forward)
+    assert list(sig.parameters) == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales", "rotations",
+                                    "cov3D_precomp", "theta", "rho"]
+    for k in ("shs", "colors_precomp", "scales", "rotations", "cov3D_precomp", "theta", "rho"):
+        assert sig.parameters[k].default is None
+    assert list(inspect.signature(dgr.rasterize_gaussians).parameters) == [
+        "means3D", "means2D", "sh", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp", "theta", "rho",
+        "raster_settings"]
+
+
+def _settings():
+    e = torch.eye(4)
+    return dgr.GaussianRasterizationSettings(image_height=32, image_width=32, tanfovx=1.0, tanfovy=1.0, bg=torch.ones(3),
+                                             scale_modifier=1.0, viewmatrix=e, projmatrix=e, projmatrix_raw=e, sh_degree=0,
+                                             campos=torch.zeros(3), prefiltered=False, debug=False)
+
+
+def test_argument_combination_errors_match_reference_messages():
+    r = dgr.GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="Please provide excatly one of either SHs or precomputed colors!"):
+        r(m, m, torch.ones(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="Please provide excatly one of either SHs or precomputed colors!"):
+        r(m, m, torch.ones(4, 1), shs=torch.ones(4, 1, 3), colors_precomp=torch.ones(4, 3), scales=torch.ones(4, 3),
+          rotations=torch.ones(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(m, m, torch.ones(4, 1), shs=torch.ones(4, 1, 3))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(m, m, torch.ones(4, 1), shs=torch.ones(4, 1, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4),
+          cov3D_precomp=torch.ones(4, 6))
+
+
+def test_no_cpu_fallback():
+    r = dgr.GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r(m, m, torch.ones(4, 1), shs=torch.ones(4, 1, 3), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        r.markVisible(m)
+
+
+def test_means3d_shape_error():
+    r = dgr.GaussianRasterizer(_settings())
+    with pytest.raises(RuntimeError, match=r"means3D must have dimensions \(num_points, 3\)"):
+        r(torch.zeros(4, 2), torch.zeros(4, 2), torch.ones(4, 1), shs=torch.ones(4, 1, 3), scales=torch.ones(4, 3),
+          rotations=torch.ones(4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "4dgs-slam_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, f)).read()
+                assert "g4r_oracle" not in text.replace("oracle/g4r_oracle.c follows", "") or f == "project.cu", (dp, f)
+                assert "import oracle" not in text and "from oracle" not in text

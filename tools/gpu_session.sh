@@ -1,0 +1,27 @@
+#!/bin/bash
+# One gpurun call = one session on the B200 box.  Every stage writes its log under gpurun_out/ and never aborts the
+# following stages.  Usage: bash tools/gpu_session.sh stage1 stage2 ...
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
+nproc >> gpurun_out/gpu_info.txt
+for stage in "$@"; do
+  echo "=== stage $stage $(date +%T)"
+  case "$stage" in
+    small)    timeout 600 python tools/gpu_check.py --golden > gpurun_out/check_small.log 2>&1; echo "rc=$?" ;;
+    big)      timeout 900 python tools/gpu_check.py --big > gpurun_out/check_big.log 2>&1; echo "rc=$?" ;;
+    pytest)   timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" ;;
+    pytestall) timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" ;;
+    smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "rc=$?" ;;
+    memcheck) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/memcheck.log 2>&1; echo "rc=$?" ;;
+    racecheck) timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/racecheck.log 2>&1; echo "rc=$?" ;;
+    bench)    timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; cat gpurun_out/bench.json ;;
+    benchref) timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches.log 2>&1; echo "rc=$?" ;;
+    ncufull)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:composite -s 4 -c 4 -o gpurun_out/prof_composite -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncufull.log 2>&1; echo "rc=$?" ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+for f in gpurun_out/check_small.log gpurun_out/pytest_gpu.log gpurun_out/check_big.log gpurun_out/smoke.log gpurun_out/memcheck.log; do
+  [ -f "$f" ] && { echo "----- tail $f"; tail -n 25 "$f"; }
+done
