@@ -15,6 +15,41 @@ int g4r_set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+// ---- per-stage profiling: thread-local, off by default ---------------------------------------------------
+struct StageProfile {
+    bool enabled = false;
+    bool created = false;
+    cudaEvent_t ev[ST_COUNT][2];
+    bool pending[ST_COUNT] = {};
+    double ms[ST_COUNT] = {};
+    int64_t count[ST_COUNT] = {};
+};
+static thread_local StageProfile g_prof;
+static const char* const k_stage_names[ST_COUNT] = {"project", "tile_scan", "scatter", "tile_sort", "composite_forward",
+                                                    "composite_backward", "gaussian_backward"};
+
+static void prof_collect() {
+    for (int i = 0; i < ST_COUNT; ++i)
+        if (g_prof.pending[i]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]) == cudaSuccess) { g_prof.ms[i] += ms; g_prof.count[i]++; }
+            g_prof.pending[i] = false;
+        }
+}
+void g4r_stage_begin(int stage, cudaStream_t s) {
+    if (!g_prof.enabled) return;
+    if (g_prof.pending[stage]) {            // the previous launch of this stage was not collected: fold it in now
+        cudaEventSynchronize(g_prof.ev[stage][1]);
+        prof_collect();
+    }
+    cudaEventRecord(g_prof.ev[stage][0], s);
+}
+void g4r_stage_end(int stage, cudaStream_t s) {
+    if (!g_prof.enabled) return;
+    cudaEventRecord(g_prof.ev[stage][1], s);
+    g_prof.pending[stage] = true;
+}
+
 struct G4RContext {
     int32_t* host_n;        // pinned
     cudaEvent_t ev;
@@ -174,6 +209,28 @@ int g4r_backward(const G4RFrame* f, const G4RGaussians* g, const int32_t* radii,
     G4R_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)g->P * G4R_ACC_STRIDE * sizeof(float), s));
     if ((rc = launch_composite_backward(*f, g->P, geom, img, binning, io->dL_dcolor, io->dL_ddepth, acc, s)) != G4R_OK) return rc;
     return launch_gaussian_backward(*f, *g, radii, geom, acc, *io, s);
+}
+
+int g4r_profile_enable(int on) {
+    if (on && !g_prof.created) {
+        for (int i = 0; i < ST_COUNT; ++i)
+            for (int j = 0; j < 2; ++j) G4R_CUDA_OK(cudaEventCreate(&g_prof.ev[i][j]));
+        g_prof.created = true;
+    }
+    g_prof.enabled = on != 0;
+    return G4R_OK;
+}
+int g4r_profile_stage_count(void) { return ST_COUNT; }
+const char* g4r_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? k_stage_names[i] : ""; }
+int g4r_profile_read(double* ms_out, int64_t* count_out, int reset) {
+    // caller must have synchronised the stream(s) the stages ran on
+    prof_collect();
+    for (int i = 0; i < ST_COUNT; ++i) {
+        if (ms_out) ms_out[i] = g_prof.ms[i];
+        if (count_out) count_out[i] = g_prof.count[i];
+        if (reset) { g_prof.ms[i] = 0.0; g_prof.count[i] = 0; }
+    }
+    return G4R_OK;
 }
 
 int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present, void* stream) {

@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(const uint32_t*
 int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
     const ImageLayout il(f.width, f.height);
     char* b = (char*)img;
+    g4r_stage_begin(ST_TILE_SCAN, s);
     tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((const uint32_t*)(b + il.counts), (uint2*)(b + il.ranges),
                                                 (uint32_t*)(b + il.header), il.tiles);
+    g4r_stage_end(ST_TILE_SCAN, s);
     G4R_LAUNCH_OK("tile_scan_kernel");
     return G4R_OK;
 }
@@ -213,12 +215,16 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
     char* bb = (char*)binning;
     const uint32_t cap = (uint32_t)(capacity > 0xffffffffll ? 0xffffffffll : capacity);
     const float4* rec = (const float4*)((const char*)geom + gl.rec);
+    g4r_stage_begin(ST_SCATTER, s);
     scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
                                                                          (uint32_t*)(ib + il.cursors), (uint2*)(bb + bl.pairs), (const uint32_t*)(ib + il.header),
                                                                          cap, (uint32_t)il.tiles_x, (uint32_t)il.tiles_y);
+    g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");
+    g4r_stage_begin(ST_TILE_SORT, s);
     tile_sort_kernel<<<il.tiles, G4R_BLOCK, 0, s>>>((const uint2*)(ib + il.ranges), (uint2*)(bb + bl.pairs), (uint2*)(bb + bl.pairs_alt),
                                                     (uint32_t*)(bb + bl.point_list), (const uint32_t*)(ib + il.header), cap);
+    g4r_stage_end(ST_TILE_SORT, s);
     G4R_LAUNCH_OK("tile_sort_kernel");
     return G4R_OK;
 }

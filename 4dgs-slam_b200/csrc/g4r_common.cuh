@@ -110,6 +110,11 @@ int g4r_set_error(int code, const char* fmt, ...);
             return g4r_set_error(G4R_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
     } while (0)
 
+// ---- optional per-stage timing (CUDA events on the launching stream; bench.py's roofline numbers) -------
+enum G4RStage { ST_PROJECT = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_COMPOSITE_FWD, ST_COMPOSITE_BWD, ST_GAUSSIAN_BWD, ST_COUNT };
+void g4r_stage_begin(int stage, cudaStream_t s);
+void g4r_stage_end(int stage, cudaStream_t s);
+
 // ---- kernel launchers (one translation unit each) ----------------------------------------
 int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* img, int32_t* radii, int32_t* n_touched,
                    cudaStream_t s);

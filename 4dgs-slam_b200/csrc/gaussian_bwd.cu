@@ -341,7 +341,9 @@ int launch_gaussian_backward(const G4RFrame& f, const G4RGaussians& g, const int
     p.dL_dmeans3D = io.dL_dmeans3D; p.dL_dmeans2D = io.dL_dmeans2D; p.dL_dopacity = io.dL_dopacity; p.dL_dshs = io.dL_dshs;
     p.dL_dcolors_precomp = io.dL_dcolors_precomp; p.dL_dscales = io.dL_dscales; p.dL_drotations = io.dL_drotations;
     p.dL_dcov3D = io.dL_dcov3D; p.dL_dtau = io.dL_dtau;
+    g4r_stage_begin(ST_GAUSSIAN_BWD, s);
     gaussian_backward_kernel<<<(g.P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(p);
+    g4r_stage_end(ST_GAUSSIAN_BWD, s);
     G4R_LAUNCH_OK("gaussian_backward_kernel");
     return G4R_OK;
 }

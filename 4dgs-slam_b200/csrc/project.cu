@@ -277,8 +277,10 @@ int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* i
     p.tile_counts = reinterpret_cast<uint32_t*>((char*)img + il.counts);
     const int blocks = (g.P + G4R_BLOCK - 1) / G4R_BLOCK;
     const bool vec = (((uintptr_t)g.means3D | (uintptr_t)g.scales | (uintptr_t)g.rotations) & 15u) == 0;
+    g4r_stage_begin(ST_PROJECT, s);
     if (vec) project_kernel<true><<<blocks, G4R_BLOCK, 0, s>>>(p);
     else     project_kernel<false><<<blocks, G4R_BLOCK, 0, s>>>(p);
+    g4r_stage_end(ST_PROJECT, s);
     G4R_LAUNCH_OK("project_kernel");
     return G4R_OK;
 }

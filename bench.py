@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (BASELINE.json metric: rasterizer fwd+bwd frames/sec @640x480, 500k Gaussians).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C2|C3sh3|C4]
+
+A *step* is one forward+backward pass of the differentiable rasterizer over one synthetic frame of the workload
+(tools/scenes.py; data = synthetic, seeded).  One JSON line is printed by rank 0:
+
+  value        frames/s with every input already resident in HBM, through the public GaussianRasterizer API
+  e2e          the same metric with HOST inputs: every step copies the frame's Gaussian tensors + camera from pinned host
+               memory to the device, runs fwd+bwd through the public API and reads the loss and the pose gradient back
+  roofline     dominant kernel: algorithmic bytes (SURVEY.md 8d terms) / its mean duration measured live with CUDA events
+               on the launching stream (g4r_profile_*), against MEASURED_PEAKS.json's HBM copy bandwidth
+  roofline_frame  whole-frame B_alg / t_step (the "fraction of HBM roofline" of BASELINE.md section 2d)
+  cpu_baseline the CPU oracle (a port: the reference has no CPU rasterizer) on the box's host cores, bounded sample
+  --impl reference  times the UNMODIFIED reference CUDA build (baseline/_ref) through its own public API on the same
+               workload; if that build is absent it times the CPU oracle port instead and says so.
+
+N > 1 (torchrun, one rank per GPU): the path shards over independent views of the same cloud (the mapping loop renders
+~10 keyframes per iteration); every rank renders its own view, no data-path collective, weak scaling; time = max over
+ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "4dgs-slam_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(P, K, N, X, tiles):
+    """SURVEY.md section 8d / BASELINE.md section 2d.  S = reference sort passes over (32 + bit) key bits."""
+    # getHigherMsb (rasterizer_impl.cu:35-50) returns the position above the MSB: 9/11/13 for 300/1200/4800 tiles
+    bit = int(tiles).bit_length()
+    S = math.ceil((32 + bit) / 8)
+    b_fwd = P * (44 + 12 * K) + 56 * P + N * (12 + 24 * S + 48) + 28 * X
+    b_bwd = N * (48 + 40) + 24 * X + P * (44 + 12 * K) + 88 * P + P * (56 + 12 * K)
+    per_kernel = {
+        "project": P * (44 + 12 * K) + 56 * P,
+        "binning": N * (12 + 24 * S),
+        "composite_forward": N * 48 + 28 * X,
+        "composite_backward": N * (48 + 40) + 24 * X,
+        "gaussian_backward": P * (44 + 12 * K) + 88 * P + P * (56 + 12 * K),
+    }
+    return b_fwd + b_bwd, per_kernel, S
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, name, seed, device):
+        from tools.scenes import config_scene
+        self.cpu = config_scene(name, seed=seed)
+        self.name = name
+        self.dev = self.cpu.to(device)
+        self.device = device
+        # pinned host copies for the end-to-end leg
+        self.host = {}
+        for k in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp", "viewmatrix", "projmatrix",
+                  "projmatrix_raw", "campos", "bg"):
+            v = getattr(self.cpu, k)
+            if v is not None:
+                self.host[k] = v.contiguous().pin_memory()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.d2h_bytes = 4 + 6 * 4                       # loss scalar + pose gradient (rho, theta)
+        self.grad_color, self.grad_depth = self.dev.grad_color, self.dev.grad_depth
+        self.result_host = torch.empty(7, dtype=torch.float32).pin_memory()
+
+
+def make_step(dgr, wl: Workload, from_host: bool):
+    """Returns fn() -> None doing one fwd+bwd through the public API of module `dgr`."""
+    sc = wl.dev
+    dev = wl.device
+
+    def settings(t):
+        return dgr.GaussianRasterizationSettings(image_height=sc.H, image_width=sc.W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=t["bg"],
+                                                 scale_modifier=sc.scale_modifier, viewmatrix=t["viewmatrix"], projmatrix=t["projmatrix"],
+                                                 projmatrix_raw=t["projmatrix_raw"], sh_degree=sc.sh_degree, campos=t["campos"],
+                                                 prefiltered=False, debug=False)
+
+    resident = {k: getattr(sc, k) for k in wl.host}
+    leaf_keys = [k for k in ("means3D", "opacities", "shs", "scales", "rotations") if k in wl.host]
+
+    def step():
+        t = {k: v.to(dev, non_blocking=True) for k, v in wl.host.items()} if from_host else resident
+        leaf = {k: t[k].detach().requires_grad_(True) for k in leaf_keys}
+        means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
+        theta = torch.zeros(3, device=dev, requires_grad=True)
+        rho = torch.zeros(3, device=dev, requires_grad=True)
+        color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(settings(t))(
+            means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], shs=leaf.get("shs"),
+            colors_precomp=t.get("colors_precomp"), scales=leaf.get("scales"), rotations=leaf.get("rotations"),
+            cov3D_precomp=t.get("cov3D_precomp"), theta=theta, rho=rho)
+        loss = (color * wl.grad_color).sum() + (depth * wl.grad_depth).sum()
+        loss.backward()
+        if from_host:
+            wl.result_host[:1].copy_(loss.detach().reshape(1), non_blocking=True)
+            wl.result_host[1:4].copy_(rho.grad, non_blocking=True)
+            wl.result_host[4:7].copy_(theta.grad, non_blocking=True)
+    return step
+
+
+def timed_steps(step, steps, warmup, flush, dist_barrier, sampler=None):
+    """W warm-ups, then K steps each bracketed by CUDA events on the current stream; L2 is flushed (outside the timed
+    region) between steps.  Returns per-step milliseconds."""
+    for _ in range(warmup):
+        step()
+        flush()
+    torch.cuda.synchronize()
+    dist_barrier()
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+        flush()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    dist_barrier()
+    return [a.elapsed_time(b) for a, b in ev], clocks
+
+
+def cpu_baseline(wl: Workload, max_frames=3, budget_s=25.0):
+    """The CPU oracle (a port of the reference algorithm) on the host cores: fwd+bwd frames/s over a bounded sample."""
+    from oracle.g4r_oracle import Oracle, scene_dict
+    ora = Oracle("f32")
+    d = scene_dict(wl.cpu)
+    t0 = time.time()
+    n = 0
+    while n < max_frames and (time.time() - t0) < budget_s:
+        f = ora.forward(d)
+        ora.backward(f, wl.cpu.grad_color, wl.cpu.grad_depth)
+        n += 1
+    dt = time.time() - t0
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} fwd+bwd frame(s) of workload {wl.name} (P={wl.cpu.P}, {wl.cpu.W}x{wl.cpu.H}) through oracle/g4r_oracle.c (OpenMP, f32)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path (the CPU oracle is only the baseline)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+        barrier = lambda: dist.barrier(device_ids=[local_rank])
+    else:
+        barrier = lambda: None
+
+    from tools import refload
+    ref_cuda = args.impl == "reference" and refload.available()
+    if args.impl == "reference" and not ref_cuda:
+        # no reference build on this box: the reference arm is the CPU port of its algorithm, rank 0 only
+        if rank == 0:
+            wl = Workload(args.workload, seed=0, device=device)
+            cb = cpu_baseline(wl, max_frames=max(1, min(args.steps, 3)))
+            print(json.dumps({"impl": "reference", "metric": "rasterizer fwd+bwd frames/sec", "value": cb["value"], "unit": "frames/s",
+                              "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": args.workload, "note": "baseline/_ref absent: CPU oracle port timed instead"},
+                              "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        if use_dist:
+            barrier()
+        return
+
+    # every rank renders its own view (seed) of the workload
+    wl = Workload(args.workload, seed=rank, device=device)
+    if ref_cuda:
+        dgr = refload.load()
+        lib = None
+    else:
+        import diff_gaussian_rasterization as dgr
+        lib = dgr._lib
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)       # > 126 MB L2
+    flush = lambda: flush_buf.zero_()
+
+    # ---- device-resident leg (value) ------------------------------------------------------------------------
+    step = make_step(dgr, wl, from_host=False)
+    if lib is not None:
+        lib.g4r_profile_enable(1)
+        n_st = lib.g4r_profile_stage_count()
+        lib.g4r_profile_stage_name.restype = ctypes.c_char_p
+    ms, clocks = timed_steps(step, args.steps, args.warmup, flush, barrier, ClockSampler(local_rank) if rank == 0 else None)
+    stage = {}
+    if lib is not None:
+        ms_arr = (ctypes.c_double * n_st)()
+        cnt_arr = (ctypes.c_int64 * n_st)()
+        lib.g4r_profile_read(ms_arr, cnt_arr, 1)
+        lib.g4r_profile_enable(0)
+        # the profile covers warm-up + timed steps alike (same work every step)
+        stage = {lib.g4r_profile_stage_name(i).decode(): (ms_arr[i] / max(1, cnt_arr[i]), int(cnt_arr[i])) for i in range(n_st)}
+    t_total = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+    if use_dist:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    total_ms = float(t_total.item())
+    value = world * args.steps / (total_ms / 1000.0)
+
+    # ---- end-to-end leg (host buffers) ------------------------------------------------------------------------
+    step_h = make_step(dgr, wl, from_host=True)
+    ms_h, _ = timed_steps(step_h, max(5, args.steps // 2), 3, flush, barrier)
+    t_h = torch.tensor([sum(ms_h)], dtype=torch.float64, device=device)
+    if use_dist:
+        dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
+    e2e_value = world * len(ms_h) / (float(t_h.item()) / 1000.0)
+
+    if rank == 0:
+        sc = wl.cpu
+        # workload statistics for the roofline: N from one extra forward
+        if lib is not None:
+            from tools import runners
+            _, info = dgr.rasterize_gaussians_with_state(runners.settings_for(wl.dev, dgr), wl.dev.means3D, wl.dev.opacities, shs=wl.dev.shs,
+                                                         colors_precomp=wl.dev.colors_precomp, scales=wl.dev.scales, rotations=wl.dev.rotations,
+                                                         cov3D_precomp=wl.dev.cov3D_precomp)
+            N = int(info["num_rendered"])
+        else:
+            N = int(refload.run_reference(wl.dev, want_grads=False)["num_rendered"])
+        K = (sc.sh_degree + 1) ** 2
+        X = sc.W * sc.H
+        tiles = ((sc.W + 15) // 16) * ((sc.H + 15) // 16)
+        b_alg, per_kernel, S = algorithmic_bytes(sc.P, K, N, X, tiles)
+        peak, peak_src = measured_peaks()
+        ms_per_step = total_ms / args.steps
+        line = {
+            "metric": "rasterizer fwd+bwd frames/sec @640x480, 500k Gaussians; HBM GB/s vs peak" if args.workload == "C3"
+                      else f"rasterizer fwd+bwd frames/sec, workload {args.workload}",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: P={sc.P} Gaussians, {sc.W}x{sc.H}, SH degree {sc.sh_degree} (M={K}), fwd+bwd incl. pose grads, "
+                                   f"num_rendered N={N}", "parallelism": f"views x{world} (independent frames per GPU, no data-path collective)",
+                       "l2": "flushed between steps (256 MiB memset outside the timed events)", "timing": "CUDA events per step on the current stream, "
+                       "sum over K steps, max over ranks", "api": "public GaussianRasterizer autograd API (Python -> ctypes -> C ABI)"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
+            "gpu_launches": 7 * args.steps if lib is not None else 0,
+            "clocks": clocks,
+            "roofline_frame": {"bound": "hbm", "algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                               "unit": "GB/s", "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                               "sort_passes_S": S},
+        }
+        if ref_cuda:
+            line["impl"] = "reference"
+            line["config"]["api"] = "UNMODIFIED reference build baseline/_ref (sm_100a) through its own GaussianRasterizer API"
+        if stage:
+            groups = {"project": ("project",), "binning": ("tile_scan", "scatter", "tile_sort"), "composite_forward": ("composite_forward",),
+                      "composite_backward": ("composite_backward",), "gaussian_backward": ("gaussian_backward",)}
+            kt = {g: sum(stage[s][0] for s in members) for g, members in groups.items()}
+            dom = max(kt, key=kt.get)
+            ach = per_kernel[dom] / (kt[dom] * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "traffic": None, "algorithmic_bytes_per_launch": per_kernel[dom], "ms_per_launch": kt[dom],
+                                "peak_source": peak_src}
+            line["kernel_ms"] = {k: round(v[0], 5) for k, v in stage.items()}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line))
+    if use_dist:
+        barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

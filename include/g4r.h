@@ -153,6 +153,15 @@ int g4r_backward(const G4RFrame* frame, const G4RGaussians* g,
 int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
 
+/* ---- optional per-stage device timing ---------------------------------------------------
+ * When enabled (per host thread), every kernel launch of this library is bracketed by CUDA events on the
+ * launching stream.  g4r_profile_read() accumulates elapsed milliseconds and launch counts per stage since the
+ * last reset; call it after synchronising the stream.  Used by bench.py for the roofline numbers. */
+int g4r_profile_enable(int on);
+int g4r_profile_stage_count(void);
+const char* g4r_profile_stage_name(int stage);
+int g4r_profile_read(double* ms_out, int64_t* count_out, int reset);
+
 /* Test / inspection hooks: byte offsets of the saved state inside the caller's buffers
  * (the parity tests read radii, point_list, ranges, n_contrib through these). */
 typedef struct G4RLayout {

@@ -12,11 +12,8 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _built():
-    """The CUDA library and the oracle are built in-tree once per session (nvcc / gcc cross-compile without a GPU)."""
+    # Build the CUDA library and the oracle in-tree BEFORE collection imports the package (nvcc / gcc cross-compile
+    # without a GPU; both are no-ops when the binaries are newer than their sources, e.g. on the GPU box).
     import __graft_entry__ as ge
     ge.build_library()
     ge.build_oracle()
