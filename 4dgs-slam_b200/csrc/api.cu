@@ -15,7 +15,7 @@ int g4r_set_error(int code, const char* fmt, ...) {
     return code;
 }
 
-// ---- per-stage profiling: thread-local, off by default ---------------------------------------------------
+// ---- per-stage profiling: process-wide, off by default (single-stream use only) ---------------------------------------------------
 struct StageProfile {
     bool enabled = false;
     bool created = false;
@@ -24,7 +24,7 @@ struct StageProfile {
     double ms[ST_COUNT] = {};
     int64_t count[ST_COUNT] = {};
 };
-static thread_local StageProfile g_prof;
+static StageProfile g_prof;   // process-wide: autograd runs backward on its own thread
 static const char* const k_stage_names[ST_COUNT] = {"project", "tile_scan", "scatter", "tile_sort", "composite_forward",
                                                     "composite_backward", "gaussian_backward"};
 
@@ -141,7 +141,7 @@ int g4r_forward_project(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* 
     cudaStream_t s = (cudaStream_t)stream;
     const ImageLayout il(f->width, f->height);
     char* ib = (char*)img;
-    // header, per-tile counts and scatter cursors are contiguous at the start of the image state
+    // header and the per-tile counters (histogram, later scatter cursors) are contiguous at the start of the image state
     G4R_CUDA_OK(cudaMemsetAsync(ib + il.header, 0, il.ranges - il.header, s));
     if (g->P > 0) {
         if ((rc = launch_project(*f, *g, geom, img, radii, n_touched, s)) != G4R_OK) return rc;
@@ -180,7 +180,7 @@ int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g
             // re-run after a capacity overflow: the aborted attempt touched nothing (every phase-2 kernel
             // exits when N > capacity), but be robust to a caller re-rendering a completed frame too.
             const ImageLayout il(f->width, f->height);
-            G4R_CUDA_OK(cudaMemsetAsync((char*)img + il.cursors, 0, (size_t)il.tiles * 4, s));
+            G4R_CUDA_OK(cudaMemsetAsync((char*)img + il.counts, 0, il.ranges - il.counts, s));
             G4R_CUDA_OK(cudaMemsetAsync(out->n_touched, 0, sizeof(int32_t) * (size_t)g->P, s));
         }
         ctx->renders_since_project++;

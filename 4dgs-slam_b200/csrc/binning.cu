@@ -23,13 +23,13 @@
 // 2. exclusive scan over tiles (single CTA; tiles <= a few 10^4)
 // ---------------------------------------------------------------------------------------------
 #define SCAN_THREADS 1024
-__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(const uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
                                                                  uint32_t* __restrict__ header, int tiles) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     const int per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
     const int t0 = threadIdx.x * per, t1 = min(tiles, t0 + per);
     uint32_t sum = 0;
-    for (int t = t0; t < t1; ++t) sum += counts[t];
+    for (int t = t0; t < t1; ++t) sum += counts[(size_t)t * G4R_COUNT_STRIDE];
     // block-wide exclusive scan of `sum`
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = sum;
@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(const uint32_t*
     __syncthreads();
     uint32_t run = s_warp[warp] + incl - sum;
     for (int t = t0; t < t1; ++t) {
-        const uint32_t c = counts[t];
+        const uint32_t c = counts[(size_t)t * G4R_COUNT_STRIDE];
+        counts[(size_t)t * G4R_COUNT_STRIDE] = 0;     // the same word becomes the scatter cursor of this tile
         ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
         run += c;
     }
@@ -64,8 +65,7 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
     const ImageLayout il(f.width, f.height);
     char* b = (char*)img;
     g4r_stage_begin(ST_TILE_SCAN, s);
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((const uint32_t*)(b + il.counts), (uint2*)(b + il.ranges),
-                                                (uint32_t*)(b + il.header), il.tiles);
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)(b + il.counts), (uint2*)(b + il.ranges), (uint32_t*)(b + il.header), il.tiles);
     g4r_stage_end(ST_TILE_SCAN, s);
     G4R_LAUNCH_OK("tile_scan_kernel");
     return G4R_OK;
@@ -76,9 +76,8 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
                                                             const uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
-                                                            uint2* __restrict__ pairs,
-                                                            const uint32_t* __restrict__ header, uint32_t capacity,
-                                                            uint32_t gx, uint32_t gy) {
+                                                            uint2* __restrict__ pairs, const uint32_t* __restrict__ header,
+                                                            uint32_t capacity, uint32_t gx, uint32_t gy) {
     if (header[0] > capacity) return;           // uniform: caller re-runs phase 2 with a larger buffer
     const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
     if (i >= P) return;
@@ -91,7 +90,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
     for (uint32_t ty = r.y0; ty < r.y1; ++ty)
         for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
             const uint32_t t = ty * gx + tx;
-            const uint32_t slot = __ldg(&ranges[t].x) + atomicAdd(cursors + t, 1u);   // cursors start at 0
+            const uint32_t slot = __ldg(&ranges[t].x) + atomicAdd(cursors + (size_t)t * G4R_COUNT_STRIDE, 1u);   // cursors start at 0
             pairs[slot] = make_uint2(key, (uint32_t)i);
         }
 }
@@ -99,13 +98,14 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
 // ---------------------------------------------------------------------------------------------
 // 4. per-tile sort by (depth bits, id)
 // ---------------------------------------------------------------------------------------------
-#define SORT_SMEM_MAX 4096                      // 32 KB of 64-bit keys
+#define SORT_SMEM_MAX 4096                      // bitonic path: 32 KB of 64-bit keys
+#define BUCKET_MAX_L 2048                       // bucket path: 2 x 16 KB of keys + 8 KB of bucket counters
+#define BUCKET_MAX_FILL 24                      // a fuller bucket sends the tile to the bitonic path
 
 // Stable LSD radix pass over one tile segment living in global memory (rare, oversized tiles).
-static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, uint32_t* __restrict__ out_ids) {
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_base[256];
+static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, uint32_t* __restrict__ out_ids, uint32_t* s_hist, uint32_t* s_base) {
     __shared__ int s_skip;
+    __shared__ uint32_t s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint2* src = a;
     uint2* dst = b;
@@ -132,7 +132,6 @@ static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, uint32_t* _
                 const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += o;
             }
-            __shared__ uint32_t s_w[8];
             if (lane == 31) s_w[warp] = incl;
             __syncthreads();
             uint32_t off = 0;
@@ -170,27 +169,9 @@ static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, uint32_t* _
     for (uint32_t e = tid; e < L; e += G4R_BLOCK) out_ids[e] = src[e].y;
 }
 
-__global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __restrict__ ranges, uint2* __restrict__ pairs,
-                                                              uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list,
-                                                              const uint32_t* __restrict__ header, uint32_t capacity) {
-    if (header[0] > capacity) return;
-    __shared__ unsigned long long s_key[SORT_SMEM_MAX];
-    const uint2 range = ranges[blockIdx.x];
-    const uint32_t L = range.y - range.x;
-    if (L == 0) return;
+// Bitonic network over n = 2^m >= L keys in shared memory (keys beyond L are +inf padding).
+static __device__ void bitonic_sort(unsigned long long* s_key, uint32_t n) {
     const int tid = threadIdx.x;
-    if (L == 1) { if (tid == 0) point_list[range.x] = pairs[range.x].y; return; }
-    if (L > SORT_SMEM_MAX) { big_tile_sort(pairs + range.x, pairs_alt + range.x, L, point_list + range.x); return; }
-
-    uint32_t n = 32;
-    while (n < L) n <<= 1;
-    for (uint32_t e = tid; e < n; e += G4R_BLOCK) {
-        unsigned long long k = ~0ull;            // padding sorts to the end
-        if (e < L) { const uint2 kv = pairs[range.x + e]; k = ((unsigned long long)kv.x << 32) | kv.y; }
-        s_key[e] = k;
-    }
-    __syncthreads();
-    // bitonic network over n = 2^m keys; n/2 comparators per stage spread over the CTA
     for (uint32_t k = 2; k <= n; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t t = tid; t < (n >> 1); t += G4R_BLOCK) {
@@ -203,6 +184,124 @@ __global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __res
             __syncthreads();
         }
     }
+}
+
+// One CTA per tile.  Fast path (L <= 2048): one-pass bucket sort -- the depth-bit range [min,max] of the tile is cut
+// into nb >= L equal integer intervals (monotone in the key), a counting placement groups the keys by bucket, and each
+// (tiny) bucket is insertion-sorted on the full 64-bit key.  ~60 instructions per key instead of ~660 for a bitonic
+// network over the next power of two.  Skewed tiles (a bucket fuller than BUCKET_MAX_FILL) and 2048 < L <= 4096 use the
+// bitonic network; larger tiles the CTA-local radix sort in global memory.  All three produce the same total order.
+__global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __restrict__ ranges, uint2* __restrict__ pairs,
+                                                              uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list,
+                                                              const uint32_t* __restrict__ header, uint32_t capacity) {
+    if (header[0] > capacity) return;
+    __shared__ __align__(16) unsigned long long s_key[SORT_SMEM_MAX];     // bucket path: [0,2048) input, [2048,4096) output
+    __shared__ uint32_t s_cnt[BUCKET_MAX_L];                               // bucket counters / cursors
+    __shared__ uint32_t s_red[2 * (G4R_BLOCK / 32)];
+    const uint2 range = ranges[blockIdx.x];
+    const uint32_t L = range.y - range.x;
+    if (L == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (L == 1) { if (tid == 0) point_list[range.x] = pairs[range.x].y; return; }
+    if (L > SORT_SMEM_MAX) { big_tile_sort(pairs + range.x, pairs_alt + range.x, L, point_list + range.x, s_cnt, s_cnt + 256); return; }
+
+    bool use_bitonic = L > BUCKET_MAX_L;
+    if (!use_bitonic) {
+        // ---- load + depth-bit range --------------------------------------------------------------------------
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
+        for (uint32_t e = tid; e < L; e += G4R_BLOCK) {
+            const uint2 kv = pairs[range.x + e];
+            s_key[e] = ((unsigned long long)kv.x << 32) | kv.y;
+            kmin = min(kmin, kv.x);
+            kmax = max(kmax, kv.x);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, d));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+        }
+        if (lane == 0) { s_red[warp] = kmin; s_red[8 + warp] = kmax; }
+        uint32_t nb = 64;
+        while (nb < L) nb <<= 1;                                         // nb in [64, 2048], nb >= L
+        for (uint32_t b = tid; b < nb; b += G4R_BLOCK) s_cnt[b] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < G4R_BLOCK / 32; ++w) { kmin = min(kmin, s_red[w]); kmax = max(kmax, s_red[8 + w]); }
+        // bucket(k) = min(nb-1, trunc(float(k - kmin) * nb / (kmax - kmin + 1))): every step (int->float rz, multiply by a
+        // positive constant rz, truncate, clamp) is monotone non-decreasing in k, which is all the sort needs.
+        const float bscale = __fdiv_rz((float)nb, __uint2float_rz(kmax - kmin) + 1.0f);
+#define BUCKET_OF(k) min(nb - 1u, __float2uint_rz(__fmul_rz(__uint2float_rz((k) - kmin), bscale)))
+        // ---- histogram ---------------------------------------------------------------------------------------
+        for (uint32_t e = tid; e < L; e += G4R_BLOCK) {
+            const uint32_t k = (uint32_t)(s_key[e] >> 32);
+            atomicAdd(&s_cnt[BUCKET_OF(k)], 1u);
+        }
+        __syncthreads();
+        // ---- exclusive scan of the nb counters (nb / 256 consecutive buckets per thread) + fill check -----------
+        const uint32_t per = nb / G4R_BLOCK;                             // 0 (nb < 256), 1, 2, 4 or 8
+        uint32_t local[8];
+        uint32_t sum = 0, worst = 0;
+        if (per == 0) {
+            local[0] = 0;
+            if (tid < (int)nb) { local[0] = s_cnt[tid]; sum = local[0]; worst = local[0]; }
+        } else {
+            for (uint32_t q = 0; q < per; ++q) { local[q] = s_cnt[tid * per + q]; sum += local[q]; worst = max(worst, local[q]); }
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        __syncthreads();                                                 // everyone is done reading s_red (min/max)
+        if (lane == 31) s_red[warp] = incl;
+        use_bitonic = __syncthreads_or(worst > BUCKET_MAX_FILL) != 0;
+        if (!use_bitonic) {
+            uint32_t off = incl - sum;
+            for (int w = 0; w < warp; ++w) off += s_red[w];
+            if (per == 0) {
+                if (tid < (int)nb) s_cnt[tid] = off;
+            } else {
+                for (uint32_t q = 0; q < per; ++q) { s_cnt[tid * per + q] = off; off += local[q]; }
+            }
+            __syncthreads();
+            // ---- counting placement into the second half of s_key (bucket cursors advance to the bucket ends) ------
+            unsigned long long* s_out = s_key + BUCKET_MAX_L;
+            for (uint32_t e = tid; e < L; e += G4R_BLOCK) {
+                const unsigned long long key = s_key[e];
+                const uint32_t k = (uint32_t)(key >> 32);
+                const uint32_t pos = atomicAdd(&s_cnt[BUCKET_OF(k)], 1u);
+                s_out[pos] = key;
+            }
+            __syncthreads();
+            // ---- insertion sort inside each bucket: bucket b = [end(b-1), end(b)) --------------------------------------
+            for (uint32_t b = tid; b < nb; b += G4R_BLOCK) {
+                const uint32_t lo = b ? s_cnt[b - 1] : 0u, hi = s_cnt[b];
+                for (uint32_t i = lo + 1; i < hi; ++i) {
+                    const unsigned long long key = s_out[i];
+                    uint32_t j = i;
+                    while (j > lo && s_out[j - 1] > key) { s_out[j] = s_out[j - 1]; --j; }
+                    s_out[j] = key;
+                }
+            }
+            __syncthreads();
+            for (uint32_t e = tid; e < L; e += G4R_BLOCK) point_list[range.x + e] = (uint32_t)s_out[e];
+            return;
+        }
+#undef BUCKET_OF
+    }
+
+    // ---- bitonic path ------------------------------------------------------------------------------------------------
+    uint32_t n = 32;
+    while (n < L) n <<= 1;
+    __syncthreads();
+    for (uint32_t e = tid; e < n; e += G4R_BLOCK) {
+        unsigned long long k = ~0ull;            // padding sorts to the end
+        if (e < L) { const uint2 kv = pairs[range.x + e]; k = ((unsigned long long)kv.x << 32) | kv.y; }
+        s_key[e] = k;
+    }
+    __syncthreads();
+    bitonic_sort(s_key, n);
     for (uint32_t e = tid; e < L; e += G4R_BLOCK) point_list[range.x + e] = (uint32_t)s_key[e];
 }
 
@@ -217,8 +316,9 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
     const float4* rec = (const float4*)((const char*)geom + gl.rec);
     g4r_stage_begin(ST_SCATTER, s);
     scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
-                                                                         (uint32_t*)(ib + il.cursors), (uint2*)(bb + bl.pairs), (const uint32_t*)(ib + il.header),
-                                                                         cap, (uint32_t)il.tiles_x, (uint32_t)il.tiles_y);
+                                                                         (uint32_t*)(ib + il.counts), (uint2*)(bb + bl.pairs),
+                                                                         (const uint32_t*)(ib + il.header), cap, (uint32_t)il.tiles_x,
+                                                                         (uint32_t)il.tiles_y);
     g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");
     g4r_stage_begin(ST_TILE_SORT, s);

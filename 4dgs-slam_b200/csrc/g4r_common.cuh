@@ -8,6 +8,9 @@
 #define G4R_BLOCK 256              // threads per CTA for every kernel in this library
 #define G4R_TILE_PIX (G4R_TILE * G4R_TILE)
 #define G4R_HEADER_WORDS 8
+// Per-tile instance counters live one per 128-byte line: atomics on neighbouring words of one line serialise in a
+// single L2 slice (measured: 1.26 M atomics on 1200 packed counters = 95 us; one counter per line = ~10x faster).
+#define G4R_COUNT_STRIDE 32
 
 // SH basis constants (values identical to DGR/cuda_rasterizer/auxiliary.h:22-39 and
 // gaussian_splatting/utils/sh_utils.py:24-41 -- they are the real SH normalisation constants).
@@ -41,7 +44,7 @@ struct GeomLayout {      // per-Gaussian state, saved for backward
     }
 };
 struct ImageLayout {     // per-pixel + per-tile state, saved for backward
-    size_t header, counts, cursors, ranges, final_T, n_contrib, total;
+    size_t header, counts, ranges, final_T, n_contrib, total;
     int tiles_x, tiles_y, tiles;
     __host__ __device__ ImageLayout(int W, int H) {
         tiles_x = (W + G4R_TILE - 1) / G4R_TILE;
@@ -49,8 +52,7 @@ struct ImageLayout {     // per-pixel + per-tile state, saved for backward
         tiles = tiles_x * tiles_y;
         size_t o = 0;
         header = o;    o = g4r_align(o + G4R_HEADER_WORDS * 4);
-        counts = o;    o = g4r_align(o + (size_t)tiles * 4);
-        cursors = o;   o = g4r_align(o + (size_t)tiles * 4);
+        counts = o;    o = g4r_align(o + (size_t)tiles * 4 * G4R_COUNT_STRIDE);   // histogram, then scatter cursors
         ranges = o;    o = g4r_align(o + (size_t)tiles * 8);
         final_T = o;   o = g4r_align(o + (size_t)W * H * 4);
         n_contrib = o; o = g4r_align(o + (size_t)W * H * 4);

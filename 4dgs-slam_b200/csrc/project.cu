@@ -226,33 +226,29 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
         cr = fmaxf(col[0], 0.0f); cg = fmaxf(col[1], 0.0f); cb = fmaxf(col[2], 0.0f);
     }
 
-    // ---- conservative footprint for warp-level culling in the composite kernels ------------------------
-    // A pixel can only receive alpha >= 1/255 from this splat if power >= -tau, tau = ln(255*opacity).
-    // (hx,hy) bound the axis-aligned extent of that ellipse; padded so that float rounding in the
-    // per-pixel evaluation can never make a culled pixel pass the reference's alpha test.
+    // ---- conservative cull threshold for the composite kernels -----------------------------------------
+    // A pixel can only receive alpha >= 1/255 from this splat if q(d) = A dx^2 + 2B dx dy + C dy^2 <= 2*ln(255*o).
+    // The composite kernels minimise q over a warp's 8x4 pixel patch and skip the splat when the minimum exceeds
+    // cull_q; the small padding absorbs float rounding of the per-pixel evaluation, so a skipped (warp, splat)
+    // pair is always one the reference would have evaluated to alpha < 1/255 for all 32 pixels.
     const float o = __ldg(p.opacities + i);
-    float ext_x = CUDART_INF_F, ext_y = CUDART_INF_F;
+    float cull_q = CUDART_INF_F;                    // no culling (degenerate conic / NaN)
     if (o < (1.0f / 255.0f)) {
-        ext_x = ext_y = -1.0f;                      // alpha = o*exp(power<=0) < 1/255 everywhere
+        cull_q = -1.0f;                             // alpha = o*exp(power<=0) < 1/255 everywhere
     } else {
         const float detq = fmaf(con_x, con_z, -con_y * con_y);
-        if (con_x > 0.0f && con_z > 0.0f && detq > 1e-4f * con_x * con_z) {
-            const float tau = fmaf(logf(255.0f * o), 1.0005f, 0.05f);
-            const float s = 2.0f * tau / detq;
-            ext_x = fmaf(sqrtf(s * con_z), 1.02f, 1.0f);
-            ext_y = fmaf(sqrtf(s * con_x), 1.02f, 1.0f);
-        }
+        if (con_x > 0.0f && con_z > 0.0f && detq > 1e-4f * con_x * con_z) cull_q = fmaf(2.0f * logf(255.0f * o), 1.002f, 0.05f);
     }
 
     float4* rec = p.rec + (size_t)i * 3;
     rec[0] = make_float4(px, py, con_x, con_y);
     rec[1] = make_float4(con_z, o, depth, cr);
-    rec[2] = make_float4(cg, cb, ext_x, ext_y);
+    rec[2] = make_float4(cg, cb, cull_q, 0.0f);
     p.radii[i] = radius_i;
 
     // ---- per-tile instance histogram (replaces tiles_touched + InclusiveSum) ----------------------------
     for (uint32_t ty_ = r.y0; ty_ < r.y1; ++ty_)
-        for (uint32_t tx_ = r.x0; tx_ < r.x1; ++tx_) atomicAdd(p.tile_counts + ty_ * p.gx + tx_, 1u);
+        for (uint32_t tx_ = r.x0; tx_ < r.x1; ++tx_) atomicAdd(p.tile_counts + (size_t)(ty_ * p.gx + tx_) * G4R_COUNT_STRIDE, 1u);
 }
 
 int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* img, int32_t* radii, int32_t* n_touched,

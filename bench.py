@@ -53,7 +53,7 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -62,13 +62,15 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = None, t1: float = None) -> dict:
+        """Samples whose timestamp falls inside the timed region [t0, t1] (host wall clock); all samples if none do."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -76,20 +78,26 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        use = inside if inside else rows
+        reasons = set()
+        for r in use:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = [r[1] for r in use]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in use) if use else None,
+                "reasons": sorted(reasons), "samples": len(use), "samples_inside_timed_region": len(inside)}
 
 
 def algorithmic_bytes(P, K, N, X, tiles):
@@ -166,13 +174,14 @@ def make_step(dgr, wl: Workload, from_host: bool):
 def timed_steps(step, steps, warmup, flush, dist_barrier, sampler=None):
     """W warm-ups, then K steps each bracketed by CUDA events on the current stream; L2 is flushed (outside the timed
     region) between steps.  Returns per-step milliseconds."""
+    if sampler:
+        sampler.start()                       # nvidia-smi needs ~0.3 s to start: launch it before the warm-up
     for _ in range(warmup):
         step()
         flush()
     torch.cuda.synchronize()
     dist_barrier()
-    if sampler:
-        sampler.start()
+    t0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in ev:
         a.record()
@@ -180,7 +189,8 @@ def timed_steps(step, steps, warmup, flush, dist_barrier, sampler=None):
         b.record()
         flush()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
     dist_barrier()
     return [a.elapsed_time(b) for a, b in ev], clocks
 
@@ -206,7 +216,7 @@ def cpu_baseline(wl: Workload, max_frames=3, budget_s=25.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")

@@ -154,7 +154,7 @@ int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
 
 /* ---- optional per-stage device timing ---------------------------------------------------
- * When enabled (per host thread), every kernel launch of this library is bracketed by CUDA events on the
+ * When enabled (process-wide; single-stream use), every kernel launch of this library is bracketed by CUDA events on the
  * launching stream.  g4r_profile_read() accumulates elapsed milliseconds and launch counts per stage since the
  * last reset; call it after synchronising the stream.  Used by bench.py for the roofline numbers. */
 int g4r_profile_enable(int on);
@@ -165,12 +165,12 @@ int g4r_profile_read(double* ms_out, int64_t* count_out, int reset);
 /* Test / inspection hooks: byte offsets of the saved state inside the caller's buffers
  * (the parity tests read radii, point_list, ranges, n_contrib through these). */
 typedef struct G4RLayout {
-    size_t geom_rec;        /* float4[3*P]: {mx,my,conic.x,conic.y} {conic.z,opacity,depth,r} {g,b,cull_hx,cull_hy} */
+    size_t geom_rec;        /* float4[3*P]: {mx,my,conic.x,conic.y} {conic.z,opacity,depth,r} {g,b,cull_q,0} */
     size_t geom_clamped;    /* uint8[P]: bit c set when SH colour channel c was clamped at 0 */
     size_t img_final_T;     /* float[H*W]    */
     size_t img_n_contrib;   /* uint32[H*W]   */
     size_t img_ranges;      /* uint2[tiles]  */
-    size_t img_counts;      /* uint32[tiles] */
+    size_t img_counts;      /* uint32[tiles*32]: one counter per 128-byte line */
     size_t img_header;      /* uint32[8]: [0] = N */
     size_t bin_point_list;  /* uint32[capacity] sorted Gaussian ids == reference point_list */
     size_t bin_pairs;       /* uint2[capacity]  unsorted (depth bits, id) */
