@@ -25,3 +25,4 @@ done
 for f in gpurun_out/check_small.log gpurun_out/pytest_gpu.log gpurun_out/check_big.log gpurun_out/smoke.log gpurun_out/memcheck.log; do
   [ -f "$f" ] && { echo "----- tail $f"; tail -n 25 "$f"; }
 done
+exit 0
