@@ -63,6 +63,8 @@ static int check_frame(const G4RFrame* f, bool backward) {
     if (!f->bg || !f->viewmatrix || !f->projmatrix || !f->campos) return g4r_set_error(G4R_EINVAL, "bg/viewmatrix/projmatrix/campos must be device pointers");
     if (backward && !f->projmatrix_raw) return g4r_set_error(G4R_EINVAL, "projmatrix_raw is required for backward");
     if (f->sh_degree < 0 || f->sh_degree > 3) return g4r_set_error(G4R_EINVAL, "sh_degree %d outside 0..3", f->sh_degree);
+    if (f->tile_world > 0 && (f->tile_rank < 0 || f->tile_rank >= f->tile_world))
+        return g4r_set_error(G4R_EINVAL, "tile_rank %d outside [0, %d)", f->tile_rank, f->tile_world);
     return G4R_OK;
 }
 
@@ -86,7 +88,7 @@ static int check_gaussians(const G4RFrame* f, const G4RGaussians* g) {
 extern "C" {
 
 const char* g4r_last_error(void) { return g_err; }
-int g4r_version(void) { return 1; }
+int g4r_version(void) { return 2; }
 
 int g4r_context_create(G4RContext** out) {
     if (!out) return g4r_set_error(G4R_EINVAL, "out is NULL");
@@ -168,7 +170,7 @@ int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g
     int rc;
     if (!ctx) return g4r_set_error(G4R_EINVAL, "context is NULL");
     if ((rc = check_frame(f, false)) != G4R_OK) return rc;
-    if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
+    if (!g || g->P < 0) return g4r_set_error(G4R_EINVAL, "gaussians is NULL or P is negative");   // phase 2 only needs P
     if (!out || !out->color || !out->depth || !out->opacity) return g4r_set_error(G4R_EINVAL, "output images are NULL");
     if (!img || !binning) return g4r_set_error(G4R_EINVAL, "img/binning buffers are NULL");
     if (g->P > 0 && (!geom || !out->radii || !out->n_touched)) return g4r_set_error(G4R_EINVAL, "geom/radii/n_touched are NULL");
@@ -189,8 +191,23 @@ int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g
     return launch_composite_forward(*f, g->P, geom, img, binning, capacity, *out, s);
 }
 
-int g4r_backward(const G4RFrame* f, const G4RGaussians* g, const int32_t* radii, const void* geom, const void* img,
-                 const void* binning, void* scratch, const G4RBackwardIO* io, void* stream) {
+int g4r_backward_composite(const G4RFrame* f, int32_t P_all, const void* geom_all, const void* img, const void* binning,
+                           const float* dL_dcolor, const float* dL_ddepth, void* scratch, void* stream) {
+    int rc;
+    if ((rc = check_frame(f, false)) != G4R_OK) return rc;
+    if (P_all <= 0) return G4R_OK;
+    if (!dL_dcolor || !dL_ddepth) return g4r_set_error(G4R_EINVAL, "dL_dcolor / dL_ddepth are NULL");
+    if (!geom_all || !img || !binning || !scratch) return g4r_set_error(G4R_EINVAL, "saved state / scratch is NULL");
+    if (((uintptr_t)geom_all | (uintptr_t)img | (uintptr_t)binning | (uintptr_t)scratch) & 15u)
+        return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* acc = (float*)scratch;
+    G4R_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)P_all * G4R_ACC_STRIDE * sizeof(float), s));
+    return launch_composite_backward(*f, P_all, geom_all, img, binning, dL_dcolor, dL_ddepth, acc, s);
+}
+
+int g4r_backward_gaussians(const G4RFrame* f, const G4RGaussians* g, const int32_t* radii, const void* geom, const void* acc,
+                           const G4RBackwardIO* io, void* stream) {
     int rc;
     if ((rc = check_frame(f, true)) != G4R_OK) return rc;
     if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
@@ -198,17 +215,55 @@ int g4r_backward(const G4RFrame* f, const G4RGaussians* g, const int32_t* radii,
     cudaStream_t s = (cudaStream_t)stream;
     G4R_CUDA_OK(cudaMemsetAsync(io->dL_dtau, 0, sizeof(float) * 8, s));
     if (g->P == 0) return G4R_OK;
-    if (!io->dL_dcolor || !io->dL_ddepth) return g4r_set_error(G4R_EINVAL, "dL_dcolor / dL_ddepth are NULL");
     if (!io->dL_dmeans3D || !io->dL_dmeans2D || !io->dL_dopacity) return g4r_set_error(G4R_EINVAL, "dL_dmeans3D/dL_dmeans2D/dL_dopacity are NULL");
     if (g->shs && !io->dL_dshs) return g4r_set_error(G4R_EINVAL, "dL_dshs is NULL although shs was given");
-    if (!radii || !geom || !img || !binning || !scratch) return g4r_set_error(G4R_EINVAL, "saved state / scratch is NULL");
-    if (((uintptr_t)geom | (uintptr_t)img | (uintptr_t)binning | (uintptr_t)scratch) & 15u)
-        return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    if (!radii || !geom || !acc) return g4r_set_error(G4R_EINVAL, "saved state / accumulators are NULL");
+    if (((uintptr_t)geom | (uintptr_t)acc) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
     if (io->dL_drotations && ((uintptr_t)io->dL_drotations & 15u)) return g4r_set_error(G4R_EINVAL, "dL_drotations must be 16-byte aligned");
-    float* acc = (float*)scratch;
-    G4R_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)g->P * G4R_ACC_STRIDE * sizeof(float), s));
-    if ((rc = launch_composite_backward(*f, g->P, geom, img, binning, io->dL_dcolor, io->dL_ddepth, acc, s)) != G4R_OK) return rc;
-    return launch_gaussian_backward(*f, *g, radii, geom, acc, *io, s);
+    return launch_gaussian_backward(*f, *g, radii, geom, (const float*)acc, *io, s);
+}
+
+int g4r_backward(const G4RFrame* f, const G4RGaussians* g, const int32_t* radii, const void* geom, const void* img,
+                 const void* binning, void* scratch, const G4RBackwardIO* io, void* stream) {
+    int rc;
+    if ((rc = check_frame(f, true)) != G4R_OK) return rc;
+    if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
+    if (!io || !io->dL_dtau) return g4r_set_error(G4R_EINVAL, "io / dL_dtau is NULL");
+    if (g->P > 0) {
+        if ((rc = g4r_backward_composite(f, g->P, geom, img, binning, io->dL_dcolor, io->dL_ddepth, scratch, stream)) != G4R_OK) return rc;
+    }
+    return g4r_backward_gaussians(f, g, radii, geom, scratch, io, stream);
+}
+
+int g4r_project_only(const G4RFrame* f, const G4RGaussians* g, void* geom, int32_t* radii, int32_t* n_touched, void* stream) {
+    int rc;
+    if ((rc = check_frame(f, false)) != G4R_OK) return rc;
+    if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
+    if (g->P == 0) return G4R_OK;
+    if (!geom || !radii || !n_touched) return g4r_set_error(G4R_EINVAL, "geom/radii/n_touched buffers are NULL");
+    if ((uintptr_t)geom & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    return launch_project(*f, *g, geom, nullptr, radii, n_touched, (cudaStream_t)stream);
+}
+
+int g4r_count_tiles(G4RContext* ctx, const G4RFrame* f, int32_t P_all, const int32_t* radii_all, const void* geom_all, void* img,
+                    void* stream) {
+    int rc;
+    if (!ctx) return g4r_set_error(G4R_EINVAL, "context is NULL");
+    if ((rc = check_frame(f, false)) != G4R_OK) return rc;
+    if (!img) return g4r_set_error(G4R_EINVAL, "img buffer is NULL");
+    if (P_all > 0 && (!radii_all || !geom_all)) return g4r_set_error(G4R_EINVAL, "radii/geom are NULL");
+    if (((uintptr_t)geom_all | (uintptr_t)img) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const ImageLayout il(f->width, f->height);
+    char* ib = (char*)img;
+    G4R_CUDA_OK(cudaMemsetAsync(ib + il.header, 0, il.ranges - il.header, s));
+    if (P_all > 0 && (rc = launch_count_tiles(*f, P_all, radii_all, geom_all, img, s)) != G4R_OK) return rc;
+    if ((rc = launch_tile_scan(*f, img, s)) != G4R_OK) return rc;
+    G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    G4R_CUDA_OK(cudaEventRecord(ctx->ev, s));
+    ctx->pending = true;
+    ctx->renders_since_project = 0;
+    return G4R_OK;
 }
 
 int g4r_profile_enable(int on) {

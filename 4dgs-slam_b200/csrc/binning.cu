@@ -77,7 +77,8 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
 __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
                                                             const uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
                                                             uint2* __restrict__ pairs, const uint32_t* __restrict__ header,
-                                                            uint32_t capacity, uint32_t gx, uint32_t gy) {
+                                                            uint32_t capacity, uint32_t gx, uint32_t gy, uint32_t tile_rank,
+                                                            uint32_t tile_world) {
     if (header[0] > capacity) return;           // uniform: caller re-runs phase 2 with a larger buffer
     const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
     if (i >= P) return;
@@ -90,9 +91,38 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
     for (uint32_t ty = r.y0; ty < r.y1; ++ty)
         for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
             const uint32_t t = ty * gx + tx;
+            if (tile_world > 1 && t % tile_world != tile_rank) continue;        // not this rank's tile
             const uint32_t slot = __ldg(&ranges[t].x) + atomicAdd(cursors + (size_t)t * G4R_COUNT_STRIDE, 1u);   // cursors start at 0
             pairs[slot] = make_uint2(key, (uint32_t)i);
         }
+}
+
+// Sharded render: per-owned-tile histogram over the all-gathered records (project_kernel's fused histogram only sees
+// the local shard).
+__global__ void __launch_bounds__(G4R_BLOCK) count_tiles_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
+                                                                uint32_t* __restrict__ counts, uint32_t gx, uint32_t gy,
+                                                                uint32_t tile_rank, uint32_t tile_world) {
+    const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
+    if (i >= P) return;
+    const int radius = radii[i];
+    if (radius <= 0) return;
+    const float4 a = ldg4(rec + (size_t)i * 3);
+    const TileRect r = tile_rect(a.x, a.y, radius, gx, gy);
+    for (uint32_t ty = r.y0; ty < r.y1; ++ty)
+        for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
+            const uint32_t t = ty * gx + tx;
+            if (t % tile_world == tile_rank) atomicAdd(counts + (size_t)t * G4R_COUNT_STRIDE, 1u);
+        }
+}
+
+int launch_count_tiles(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, cudaStream_t s) {
+    const GeomLayout gl(P);
+    const ImageLayout il(f.width, f.height);
+    count_tiles_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(
+        P, radii, (const float4*)((const char*)geom + gl.rec), (uint32_t*)((char*)img + il.counts), (uint32_t)il.tiles_x,
+        (uint32_t)il.tiles_y, g4r_tile_rank(f), g4r_tile_world(f));
+    G4R_LAUNCH_OK("count_tiles_kernel");
+    return G4R_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,7 +348,7 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
     scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
                                                                          (uint32_t*)(ib + il.counts), (uint2*)(bb + bl.pairs),
                                                                          (const uint32_t*)(ib + il.header), cap, (uint32_t)il.tiles_x,
-                                                                         (uint32_t)il.tiles_y);
+                                                                         (uint32_t)il.tiles_y, g4r_tile_rank(f), g4r_tile_world(f));
     g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");
     g4r_stage_begin(ST_TILE_SORT, s);

@@ -117,11 +117,15 @@ enum G4RStage { ST_PROJECT = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_COMPO
 void g4r_stage_begin(int stage, cudaStream_t s);
 void g4r_stage_end(int stage, cudaStream_t s);
 
+static inline uint32_t g4r_tile_world(const G4RFrame& f) { return f.tile_world > 0 ? (uint32_t)f.tile_world : 1u; }
+static inline uint32_t g4r_tile_rank(const G4RFrame& f) { return f.tile_world > 0 ? (uint32_t)f.tile_rank : 0u; }
+
 // ---- kernel launchers (one translation unit each) ----------------------------------------
 int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* img, int32_t* radii, int32_t* n_touched,
                    cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s);
+int launch_count_tiles(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, cudaStream_t s);
 int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
                         int64_t capacity, cudaStream_t s);
 int launch_composite_forward(const G4RFrame& f, int P, const void* geom, void* img, const void* binning, int64_t capacity,

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     p.radii[i] = radius_i;
 
     // ---- per-tile instance histogram (replaces tiles_touched + InclusiveSum) ----------------------------
+    if (p.tile_counts == nullptr) return;           // sharded render: tiles are counted after the all-gather
     for (uint32_t ty_ = r.y0; ty_ < r.y1; ++ty_)
         for (uint32_t tx_ = r.x0; tx_ < r.x1; ++tx_) atomicAdd(p.tile_counts + (size_t)(ty_ * p.gx + tx_) * G4R_COUNT_STRIDE, 1u);
 }
@@ -270,7 +271,7 @@ int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* i
     p.clamped = reinterpret_cast<uint8_t*>((char*)geom + gl.clamped);
     p.radii = radii;
     p.n_touched = n_touched;
-    p.tile_counts = reinterpret_cast<uint32_t*>((char*)img + il.counts);
+    p.tile_counts = img ? reinterpret_cast<uint32_t*>((char*)img + il.counts) : nullptr;
     const int blocks = (g.P + G4R_BLOCK - 1) / G4R_BLOCK;
     const bool vec = (((uintptr_t)g.means3D | (uintptr_t)g.scales | (uintptr_t)g.rotations) & 15u) == 0;
     g4r_stage_begin(ST_PROJECT, s);

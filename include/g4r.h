@@ -67,6 +67,10 @@ typedef struct G4RFrame {
     const float* projmatrix;      /* [16] */
     const float* projmatrix_raw;  /* [16] backward only (pose Jacobian); may be NULL in forward */
     const float* campos;          /* [3]  */
+    /* Tile ownership for the Gaussian-sharded multi-GPU render: phase 2 and the backward composite only touch tiles t
+     * with t % tile_world == tile_rank.  Single GPU: tile_rank = 0, tile_world = 1 (a zeroed tile_world means 1). */
+    int32_t tile_rank;
+    int32_t tile_world;
 } G4RFrame;
 
 /* Per-Gaussian inputs (all DEVICE pointers, contiguous, read-only). */
@@ -111,7 +115,7 @@ typedef struct G4RContext G4RContext;   /* owns one pinned int + one event; one 
 
 /* ---- library / context ------------------------------------------------------------ */
 const char* g4r_last_error(void);
-int  g4r_version(void);                               /* ABI version, currently 1 */
+int  g4r_version(void);                               /* ABI version, currently 2 */
 int  g4r_context_create(G4RContext** out);
 void g4r_context_destroy(G4RContext* ctx);
 
@@ -148,6 +152,22 @@ int64_t g4r_wait_num_rendered(G4RContext* ctx);
 int g4r_backward(const G4RFrame* frame, const G4RGaussians* g,
                  const int32_t* radii, const void* geom, const void* img, const void* binning,
                  void* scratch, const G4RBackwardIO* io, void* stream);
+
+/* ---- building blocks of the Gaussian-sharded multi-GPU render ------------
+ * Each rank projects its own shard (g4r_project_only), the 48-byte splat records + radii of all shards are all-gathered
+ * by the caller (NCCL), and every rank bins / sorts / composites only the tiles it owns (frame->tile_rank/tile_world):
+ *   g4r_count_tiles  : per-owned-tile histogram over ALL gathered records + tile scan + async copy of N (like phase 1)
+ *   g4r_forward_render (above) then scatters / sorts / composites the owned tiles; other pixels are left untouched
+ *   g4r_backward_composite : zeroes `acc` ([P_all,12] floats) and accumulates the owned tiles' screen-space gradients
+ *   g4r_backward_gaussians : per-Gaussian backward of one shard from its (reduce-scattered) accumulator rows
+ * g4r_backward == g4r_backward_composite + g4r_backward_gaussians on one GPU. */
+int g4r_project_only(const G4RFrame* frame, const G4RGaussians* g, void* geom, int32_t* radii, int32_t* n_touched, void* stream);
+int g4r_count_tiles(G4RContext* ctx, const G4RFrame* frame, int32_t P_all, const int32_t* radii_all, const void* geom_all,
+                    void* img, void* stream);
+int g4r_backward_composite(const G4RFrame* frame, int32_t P_all, const void* geom_all, const void* img, const void* binning,
+                           const float* dL_dcolor, const float* dL_ddepth, void* acc, void* stream);
+int g4r_backward_gaussians(const G4RFrame* frame, const G4RGaussians* g, const int32_t* radii, const void* geom,
+                           const void* acc, const G4RBackwardIO* io, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------- */
 int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

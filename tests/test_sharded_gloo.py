@@ -1,0 +1,223 @@
+"""N > 1 host logic of the Gaussian-sharded render, on CPU with the gloo backend and world_size 2.
+
+The product runs the CUDA kernels (diff_gaussian_rasterization.sharded.CudaBackend); here a test-only backend built on
+the CPU oracle stands in for the five kernel groups so that shard bounds, padding, tile ownership and the collective
+sequence (all-gather records -> owned-tile composite -> all-reduce image / reduce-scatter gradients) can be checked
+against the single-process oracle without a GPU."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    """CPU stand-in for the kernel groups (TEST ONLY)."""
+
+    def __init__(self):
+        from oracle.g4r_oracle import Oracle
+        self.o = Oracle("f32")
+        self.local = None
+
+    def image_state_bytes(self, W, H):
+        return 64
+
+    def geom_state_bytes(self, P):
+        return P * 48 + 512
+
+    @staticmethod
+    def _scene(rs, **kw):
+        d = dict(W=int(rs.image_width), H=int(rs.image_height), sh_degree=int(rs.sh_degree), tanfovx=rs.tanfovx, tanfovy=rs.tanfovy,
+                 scale_modifier=rs.scale_modifier, bg=rs.bg, viewmatrix=rs.viewmatrix, projmatrix=rs.projmatrix,
+                 projmatrix_raw=rs.projmatrix_raw, campos=rs.campos)
+        d.update(kw)
+        return d
+
+    def project(self, rs, M, tile_rank, tile_world, means3D, opacities, sh, colors, scales, rots, cov, geom, radii, n_touched):
+        nz = lambda t: t if t.numel() else None
+        sc = self._scene(rs, means3D=means3D, opacities=opacities, shs=nz(sh), colors_precomp=nz(colors), scales=nz(scales),
+                         rotations=nz(rots), cov3D_precomp=nz(cov))
+        S, keep, P, M_ = self.o._pack(sc)
+        from oracle.g4r_oracle import _Geom, _p
+        dt = np.float32
+        g = dict(depths=np.zeros(P, dt), means2D=np.zeros((P, 2), dt), cov3D=np.zeros((P, 6), dt), conic_opacity=np.zeros((P, 4), dt),
+                 rgb=np.zeros((P, 3), dt), clamped=np.zeros((P, 3), np.uint8), radii=np.zeros(P, np.int32), tiles_touched=np.zeros(P, np.uint32))
+        G = _Geom(*[_p(g[k]) for k in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "radii", "tiles_touched")])
+        self.o._project(ctypes.byref(S), ctypes.byref(G))
+        rgb = keep["colors_precomp"] if keep["colors_precomp"] is not None else g["rgb"]
+        rec = np.zeros((P, 12), dt)
+        rec[:, 0:2], rec[:, 2:4], rec[:, 4], rec[:, 5] = g["means2D"], g["conic_opacity"][:, :2], g["conic_opacity"][:, 2], g["conic_opacity"][:, 3]
+        rec[:, 6], rec[:, 7:10] = g["depths"], rgb
+        geom[: P * 48].view(torch.float32).view(P, 12).copy_(torch.from_numpy(rec))
+        radii[:P].copy_(torch.from_numpy(g["radii"]))
+        self.local = (sc, g)
+
+    def _all_scene(self, rs, rec_all, radii_all):
+        rec = rec_all.numpy()
+        P = rec.shape[0]
+        from oracle.g4r_oracle import _Geom, _p
+        g = dict(depths=np.ascontiguousarray(rec[:, 6]), means2D=np.ascontiguousarray(rec[:, 0:2]), cov3D=np.zeros((P, 6), np.float32),
+                 conic_opacity=np.ascontiguousarray(np.concatenate([rec[:, 2:5], rec[:, 5:6]], 1)), rgb=np.ascontiguousarray(rec[:, 7:10]),
+                 clamped=np.zeros((P, 3), np.uint8), radii=np.ascontiguousarray(radii_all.numpy()), tiles_touched=np.zeros(P, np.uint32))
+        sc = self._scene(rs, means3D=np.zeros((P, 3), np.float32), opacities=np.zeros((P, 1), np.float32), colors_precomp=g["rgb"],
+                         cov3D_precomp=g["cov3D"])
+        S, keep, _, _ = self.o._pack(sc)
+        G = _Geom(*[_p(g[k]) for k in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "radii", "tiles_touched")])
+        return S, keep, G, g
+
+    def render(self, rs, tile_rank, tile_world, P_all, rec_all, radii_all, n_touched_all, images, img_state, cap_hint):
+        from oracle.g4r_oracle import _p
+        S, keep, G, g = self._all_scene(rs, rec_all, radii_all)
+        W, H = S.W, S.H
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        # tiles_touched from the rectangles (oracle_bin needs it): recompute through a throw-away pass of get_rect semantics
+        tt = np.zeros(P_all, np.uint32)
+        r = g["radii"]
+        px, py = g["means2D"][:, 0], g["means2D"][:, 1]
+        rf = r.astype(np.float32)
+        f2i = lambda v: np.clip(np.trunc(v), -2**31, 2**31 - 1).astype(np.int64)
+        x0 = np.minimum(gx, np.maximum(0, f2i((px - rf) * np.float32(0.0625))))
+        y0 = np.minimum(gy, np.maximum(0, f2i((py - rf) * np.float32(0.0625))))
+        x1 = np.minimum(gx, np.maximum(0, f2i((((px + rf) + np.float32(16)) + np.float32(-1)) * np.float32(0.0625))))
+        y1 = np.minimum(gy, np.maximum(0, f2i((((py + rf) + np.float32(16)) + np.float32(-1)) * np.float32(0.0625))))
+        tt[:] = np.where(r > 0, (x1 - x0) * (y1 - y0), 0)
+        g["tiles_touched"][:] = tt
+        pl_ptr = ctypes.c_void_p()
+        ranges = np.zeros((gx * gy, 2), np.uint32)
+        N = int(self.o._bin(ctypes.byref(S), ctypes.byref(G), ctypes.byref(pl_ptr), ctypes.c_void_p(_p(ranges))))
+        pl = np.ctypeslib.as_array(ctypes.cast(pl_ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(max(N, 1),))[:N].copy()
+        self.o._free(pl_ptr)
+        owned = (np.arange(gx * gy) % tile_world) == tile_rank
+        ranges[~owned] = 0                                     # this rank composites only its tiles
+        color, depth, opac = np.zeros((3, H, W), np.float32), np.zeros((1, H, W), np.float32), np.zeros((1, H, W), np.float32)
+        final_T, n_contrib, n_touched = np.zeros((H, W), np.float32), np.zeros((H, W), np.uint32), np.zeros(P_all, np.int32)
+        plc = np.ascontiguousarray(pl if N else np.zeros(1, np.uint32))
+        self.o._composite(ctypes.byref(S), ctypes.byref(G), ctypes.c_void_p(_p(plc)), ctypes.c_void_p(_p(ranges)), ctypes.c_void_p(_p(color)),
+                          ctypes.c_void_p(_p(depth)), ctypes.c_void_p(_p(opac)), ctypes.c_void_p(_p(final_T)), ctypes.c_void_p(_p(n_contrib)),
+                          ctypes.c_void_p(_p(n_touched)))
+        # pixels of tiles this rank does not own stay zero
+        tile_of_pixel = (np.arange(H)[:, None] // 16) * gx + (np.arange(W)[None, :] // 16)
+        mask = owned[tile_of_pixel]
+        images[0:3].copy_(torch.from_numpy(color * mask))
+        images[3:4].copy_(torch.from_numpy(depth * mask))
+        images[4:5].copy_(torch.from_numpy(opac * mask))
+        n_touched_all.copy_(torch.from_numpy(n_touched))
+        state = dict(pl=plc, ranges=ranges, final_T=final_T, n_contrib=n_contrib, N=N)
+        return state, N
+
+    def composite_backward(self, rs, tile_rank, tile_world, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):
+        from oracle.g4r_oracle import _p
+        st = binning
+        S, keep, G, g = self._all_scene(rs, rec_all, torch.from_numpy(self._radii_all))
+        acc = np.zeros((P_all, 10), np.float64)
+        gc = np.ascontiguousarray(grad_color.numpy().astype(np.float32))
+        gd = np.ascontiguousarray(grad_depth.numpy().astype(np.float32))
+        self.o._composite_bw(ctypes.byref(S), ctypes.byref(G), ctypes.c_void_p(_p(st["pl"])), ctypes.c_void_p(_p(st["ranges"])),
+                             ctypes.c_void_p(_p(st["final_T"])), ctypes.c_void_p(_p(st["n_contrib"])), ctypes.c_void_p(_p(gc)),
+                             ctypes.c_void_p(_p(gd)), ctypes.c_void_p(_p(acc)))
+        out = np.zeros((P_all, 12), np.float32)
+        out[:, :10] = acc
+        acc_all.copy_(torch.from_numpy(out))
+
+    def gaussian_backward(self, rs, M, means3D, sh, colors, scales, rots, cov, radii, geom, acc, grads, tau):
+        from oracle.g4r_oracle import _Geom, _Grads, _p
+        sc, g = self.local
+        S, keep, P, M_ = self.o._pack(sc)
+        G = _Geom(*[_p(g[k]) for k in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "radii", "tiles_touched")])
+        a = np.ascontiguousarray(acc.numpy()[:P, :10].astype(np.float64))
+        dt = np.float32
+        o = dict(dL_dmeans3D=np.zeros((P, 3), dt), dL_dmeans2D=np.zeros((P, 3), dt), dL_dopacity=np.zeros(P, dt), dL_dcolors=np.zeros((P, 3), dt),
+                 dL_dcov3D=np.zeros((P, 6), dt), dL_dshs=np.zeros((P, max(M_, 1), 3), dt) if keep["shs"] is not None else None,
+                 dL_dscales=np.zeros((P, 3), dt) if keep["scales"] is not None else None,
+                 dL_drots=np.zeros((P, 4), dt) if keep["scales"] is not None else None, dL_dtau_rows=np.zeros((P, 6), dt), dL_dtau=np.zeros(6, dt))
+        GR = _Grads(*[_p(o[k]) for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dopacity", "dL_dcolors", "dL_dcov3D", "dL_dshs", "dL_dscales", "dL_drots",
+                                         "dL_dtau_rows", "dL_dtau")])
+        self.o._gaussian_bw(ctypes.byref(S), ctypes.byref(G), ctypes.c_void_p(_p(a)), ctypes.byref(GR))
+        grads["means3D"].copy_(torch.from_numpy(o["dL_dmeans3D"]))
+        grads["means2D"].copy_(torch.from_numpy(o["dL_dmeans2D"]))
+        grads["opacities"].copy_(torch.from_numpy(o["dL_dopacity"]).view(grads["opacities"].shape))
+        if "sh" in grads:
+            grads["sh"].copy_(torch.from_numpy(o["dL_dshs"]))
+        if "scales" in grads:
+            grads["scales"].copy_(torch.from_numpy(o["dL_dscales"]))
+            grads["rots"].copy_(torch.from_numpy(o["dL_drots"]))
+        tau[:6].copy_(torch.from_numpy(o["dL_dtau"]))
+
+
+def _worker(rank, world, port, P, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import diff_gaussian_rasterization as dgr
+    from diff_gaussian_rasterization import sharded
+    from tools.scenes import make_scene
+    # the CPU test backend bypasses the CUDA-only checks of the product module
+    sharded._dev_f32 = lambda t, dev: t.float().contiguous()
+    sc = make_scene(P, 96, 64, sh_degree=1, seed=11)
+    lo, hi = sharded.shard_bounds(P, world, rank)
+    rs = dgr.GaussianRasterizationSettings(image_height=sc.H, image_width=sc.W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=sc.bg,
+                                           scale_modifier=1.0, viewmatrix=sc.viewmatrix, projmatrix=sc.projmatrix,
+                                           projmatrix_raw=sc.projmatrix_raw, sh_degree=sc.sh_degree, campos=sc.campos, prefiltered=False, debug=False)
+    be = OracleBackend()
+    orig_render = be.render
+
+    def render(rs_, tr, tw, P_all, rec_all, radii_all, *a):
+        be._radii_all = radii_all.numpy().copy()
+        return orig_render(rs_, tr, tw, P_all, rec_all, radii_all, *a)
+    be.render = render
+    leaf = {k: getattr(sc, k)[lo:hi].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
+    theta, rho = torch.zeros(3, requires_grad=True), torch.zeros(3, requires_grad=True)
+    r = sharded.ShardedGaussianRasterizer(rs, backend=be)
+    color, radii, depth, opacity, n_touched = r(means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf["shs"],
+                                                scales=leaf["scales"], rotations=leaf["rotations"], theta=theta, rho=rho)
+    ((color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()).backward()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), color=color.detach().numpy(), depth=depth.detach().numpy(), opacity=opacity.detach().numpy(),
+             radii=radii.numpy(), n_touched=n_touched.numpy(), lo=lo, hi=hi, means3D=leaf["means3D"].grad.numpy(),
+             scales=leaf["scales"].grad.numpy(), rots=leaf["rotations"].grad.numpy(), opac=leaf["opacities"].grad.numpy(),
+             shs=leaf["shs"].grad.numpy(), m2d=m2d.grad.numpy(), theta=theta.grad.numpy(), rho=rho.grad.numpy())
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_partition():
+    from diff_gaussian_rasterization.sharded import shard_bounds, owned_tiles
+    for P in (0, 1, 7, 100, 1001):
+        for world in (1, 2, 3, 8):
+            edges = [shard_bounds(P, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == P
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in edges) - min(h - l for l, h in edges) <= 1
+    masks = torch.stack([owned_tiles(640, 480, 4, r) for r in range(4)])
+    assert bool((masks.sum(0) == 1).all())
+
+
+@pytest.mark.parametrize("P", [1500, 1501])
+def test_sharded_render_matches_single_process_oracle(tmp_path, P):
+    world = 2
+    port = 29000 + os.getpid() % 2000 + P % 7
+    mp.spawn(_worker, args=(world, port, P, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, ROOT)
+    from tools import runners
+    from tools.scenes import make_scene
+    sc = make_scene(P, 96, 64, sh_degree=1, seed=11)
+    ref = runners.run_oracle(sc)
+    parts = [np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(world)]
+    for z in parts:                                            # every rank holds the full, identical image
+        assert np.array_equal(z["color"], ref["color"]) and np.array_equal(z["depth"], ref["depth"])
+        assert np.array_equal(z["opacity"], ref["opacity"])
+    cat = lambda k: np.concatenate([z[k] for z in parts], 0)
+    assert np.array_equal(cat("radii"), ref["radii"]) and np.array_equal(cat("n_touched"), ref["n_touched"])
+    for k, rk in (("means3D", "dL_dmeans3D"), ("scales", "dL_dscales"), ("rots", "dL_drots"), ("shs", "dL_dshs"), ("m2d", "dL_dmeans2D")):
+        a, b = cat(k).astype(np.float64), ref[rk].astype(np.float64)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-5, k
+    assert np.allclose(cat("opac").reshape(-1), ref["dL_dopacity"], rtol=1e-4, atol=1e-9)
+    tau = np.concatenate([parts[0]["rho"].reshape(-1), parts[0]["theta"].reshape(-1)])
+    assert np.allclose(tau, ref["dL_dtau"], rtol=1e-4, atol=1e-8)
+    assert np.array_equal(parts[0]["theta"], parts[1]["theta"])
