@@ -89,6 +89,10 @@ extern "C" {
 
 const char* g4r_last_error(void) { return g_err; }
 int g4r_version(void) { return 2; }
+void g4r_struct_sizes(int32_t* out5) {
+    out5[0] = (int32_t)sizeof(G4RFrame); out5[1] = (int32_t)sizeof(G4RGaussians); out5[2] = (int32_t)sizeof(G4RForwardOut);
+    out5[3] = (int32_t)sizeof(G4RBackwardIO); out5[4] = (int32_t)sizeof(G4RLayout);
+}
 
 int g4r_context_create(G4RContext** out) {
     if (!out) return g4r_set_error(G4R_EINVAL, "out is NULL");

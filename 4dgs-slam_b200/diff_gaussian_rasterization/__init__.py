@@ -47,6 +47,7 @@ class _Frame(ctypes.Structure):
         ("sh_degree", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32), ("prefiltered", ctypes.c_int32),
         ("bg", ctypes.c_void_p), ("viewmatrix", ctypes.c_void_p), ("projmatrix", ctypes.c_void_p),
         ("projmatrix_raw", ctypes.c_void_p), ("campos", ctypes.c_void_p),
+        ("tile_rank", ctypes.c_int32), ("tile_world", ctypes.c_int32),
     ]
 
 
@@ -120,6 +121,15 @@ def _load_library() -> ctypes.CDLL:
     lib.g4r_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.g4r_layout.restype = ctypes.c_int
     lib.g4r_layout.argtypes = [i32, i32, i32, i64, ctypes.POINTER(_Layout)]
+    # the ctypes mirrors above must have exactly the C layout of include/g4r.h
+    sizes = (ctypes.c_int32 * 5)()
+    lib.g4r_struct_sizes(sizes)
+    mine = [ctypes.sizeof(c) for c in (_Frame, _Gaussians, _ForwardOut, _BackwardIO, _Layout)]
+    if list(sizes) != mine:
+        raise ImportError(f"diff_gaussian_rasterization: struct layout mismatch between libg4r.so {list(sizes)} and the Python "
+                          f"bindings {mine}; rebuild the library")
+    if lib.g4r_version() != 2:
+        raise ImportError(f"diff_gaussian_rasterization: libg4r.so has ABI version {lib.g4r_version()}, expected 2; rebuild it")
     return lib
 
 
@@ -179,6 +189,7 @@ def _make_frame(rs: "GaussianRasterizationSettings", device: torch.device, sh_co
     f.prefiltered = int(bool(rs.prefiltered))
     f.bg, f.viewmatrix, f.projmatrix = mat(rs.bg), mat(rs.viewmatrix), mat(rs.projmatrix)
     f.projmatrix_raw, f.campos = mat(rs.projmatrix_raw), mat(rs.campos)
+    f.tile_rank, f.tile_world = 0, 1
     return f
 
 

@@ -116,6 +116,7 @@ typedef struct G4RContext G4RContext;   /* owns one pinned int + one event; one 
 /* ---- library / context ------------------------------------------------------------ */
 const char* g4r_last_error(void);
 int  g4r_version(void);                               /* ABI version, currently 2 */
+void g4r_struct_sizes(int32_t* out5);                 /* sizeof {G4RFrame, G4RGaussians, G4RForwardOut, G4RBackwardIO, G4RLayout}: FFI self-check */
 int  g4r_context_create(G4RContext** out);
 void g4r_context_destroy(G4RContext* ctx);
 

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_sizes():
     lib = ctypes.CDLL(LIB)
-    assert lib.g4r_version() == 1
+    assert lib.g4r_version() == 2
     for f in (lib.g4r_geom_bytes, lib.g4r_binning_bytes, lib.g4r_backward_scratch_bytes, lib.g4r_image_bytes):
         f.restype = ctypes.c_size_t
     lib.g4r_geom_bytes.argtypes = [ctypes.c_int32]
@@ -66,6 +66,14 @@ def test_bad_arguments_are_reported_not_crashed():
     assert lib.g4r_mark_visible(0, None, None, None, None, None) == 0
     lib.g4r_wait_num_rendered.restype = ctypes.c_int64
     assert lib.g4r_wait_num_rendered(None) == -1
+
+
+def test_python_struct_mirrors_match_the_c_layout():
+    import diff_gaussian_rasterization as dgr
+    sizes = (ctypes.c_int32 * 5)()
+    dgr._lib.g4r_struct_sizes(sizes)
+    assert list(sizes) == [ctypes.sizeof(c) for c in (dgr._Frame, dgr._Gaussians, dgr._ForwardOut, dgr._BackwardIO, dgr._Layout)]
+    assert [n for n, _ in dgr._Frame._fields_][-2:] == ["tile_rank", "tile_world"]
 
 
 def test_layout_offsets_are_aligned_and_ordered():
