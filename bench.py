@@ -402,8 +402,17 @@ def main():
             kt = {g: sum(stage[s][0] for s in members) for g, members in groups.items()}
             dom = max(kt, key=kt.get)
             ach = per_kernel[dom] / (kt[dom] * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath) and args.workload == "C3":
+                # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture
+                with open(tpath) as f:
+                    tj = json.load(f)
+                for kname, kv in tj["kernels"].items():
+                    if dom in kname or (dom == "binning" and "tile_sort" in kname):
+                        traffic = kv["dram_bytes_per_launch"]
             line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": None, "algorithmic_bytes_per_launch": per_kernel[dom], "ms_per_launch": kt[dom],
+                                "traffic": traffic, "algorithmic_bytes_per_launch": per_kernel[dom], "ms_per_launch": kt[dom],
                                 "peak_source": peak_src}
             line["kernel_ms"] = {k: round(v[0], 5) for k, v in stage.items()}
         if not args.no_cpu_baseline:

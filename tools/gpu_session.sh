@@ -16,10 +16,10 @@ for stage in "$@"; do
     memcheck) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/memcheck.log 2>&1; echo "rc=$?" ;;
     racecheck) timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/racecheck.log 2>&1; echo "rc=$?" ;;
     bench)    timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; cat gpurun_out/bench.json ;;
-    benchv1)  G4R_FWD_V1=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_fwdv1.json 2> gpurun_out/bench_fwdv1.err; echo "rc=$?"; cat gpurun_out/bench_fwdv1.json ;;
     benchref) timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches.log 2>&1; echo "rc=$?" ;;
     ncufull)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:composite -s 4 -c 4 -o gpurun_out/prof_composite -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncufull.log 2>&1; echo "rc=$?" ;;
+    ncuall)   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'project_kernel|tile_scan|scatter_kernel|tile_sort|composite|gaussian_backward' -s 21 -c 7 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncuall.log 2>&1; echo "rc=$?" ;;
     sharded2) for wl in C2 C4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py --workload $wl > gpurun_out/sharded_$wl.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_$wl.log; done ;;
     bench2)   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 100 --no-cpu-baseline > gpurun_out/bench_x2.json 2> gpurun_out/bench_x2.err; echo "rc=$?"; cat gpurun_out/bench_x2.json ;;
     *) echo "unknown stage $stage" ;;
