@@ -33,8 +33,11 @@ struct V3 { float x, y, z; };
 static __device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 static __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
-__global__ void __launch_bounds__(G4R_BLOCK) gaussian_backward_kernel(const GaussBwdParams p) {
+__global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const GaussBwdParams p) {
     __shared__ float s_tau[G4R_BLOCK / 32][6];
+    __shared__ float v[16], pm[16];      // view / full projection matrices: broadcast reads instead of 32 live registers
+    if (threadIdx.x < 16) { v[threadIdx.x] = __ldg(p.viewmatrix + threadIdx.x); pm[threadIdx.x] = __ldg(p.projmatrix + threadIdx.x); }
+    __syncthreads();
     const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float tau[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -57,10 +60,6 @@ __global__ void __launch_bounds__(G4R_BLOCK) gaussian_backward_kernel(const Gaus
     }
 
     if (visible) {
-        const float* __restrict__ V = p.viewmatrix;
-        float v[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = __ldg(V + k);
         const float mx = __ldg(p.means3D + (size_t)i * 3), my = __ldg(p.means3D + (size_t)i * 3 + 1), mz = __ldg(p.means3D + (size_t)i * 3 + 2);
 
         // accumulated screen-space gradients from composite_backward_kernel
@@ -164,10 +163,6 @@ __global__ void __launch_bounds__(G4R_BLOCK) gaussian_backward_kernel(const Gaus
         }
 
         // ---- 2D mean -> 3D mean and pose (backward.cu:446-512) -----------------------------------------
-        const float* __restrict__ Pm = p.projmatrix;
-        float pm[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) pm[k] = __ldg(Pm + k);
         const float hx = pm[0] * mx + pm[4] * my + pm[8] * mz + pm[12];
         const float hy = pm[1] * mx + pm[5] * my + pm[9] * mz + pm[13];
         const float hw = pm[3] * mx + pm[7] * my + pm[11] * mz + pm[15];
