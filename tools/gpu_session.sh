@@ -26,6 +26,7 @@ for stage in "$@"; do
                 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 100 --no-cpu-baseline > gpurun_out/bench_x$n.json 2> gpurun_out/bench_x$n.err; echo "bench x$n rc=$?"; cut -c1-200 gpurun_out/bench_x$n.json
                 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n tools/sharded_check.py --workload C4 > gpurun_out/sharded_C4_x$n.log 2>&1; echo "sharded C4 x$n rc=$?"; tail -2 gpurun_out/sharded_C4_x$n.log | cut -c1-400
               done ;;
+    matrix)   timeout 900 python tools/perf_matrix.py > gpurun_out/perf_matrix.log 2>&1; echo "rc=$?"; cat gpurun_out/perf_matrix.log | cut -c1-400 ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
