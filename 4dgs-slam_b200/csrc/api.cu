@@ -138,7 +138,7 @@ int g4r_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, G4RLayout* out
 int g4r_forward_project(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g, void* geom, void* img, int32_t* radii,
                         int32_t* n_touched, void* stream) {
     int rc;
-    if (!ctx) return g4r_set_error(G4R_EINVAL, "context is NULL");
+    // ctx == NULL: no read-back of N (CUDA-graph capture: the caller guarantees the capacity handed to phase 2)
     if ((rc = check_frame(f, false)) != G4R_OK) return rc;
     if ((rc = check_gaussians(f, g)) != G4R_OK) return rc;
     if (!img) return g4r_set_error(G4R_EINVAL, "img buffer is NULL");
@@ -153,10 +153,12 @@ int g4r_forward_project(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* 
         if ((rc = launch_project(*f, *g, geom, img, radii, n_touched, s)) != G4R_OK) return rc;
     }
     if ((rc = launch_tile_scan(*f, img, s)) != G4R_OK) return rc;
-    G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    G4R_CUDA_OK(cudaEventRecord(ctx->ev, s));
-    ctx->pending = true;
-    ctx->renders_since_project = 0;
+    if (ctx) {
+        G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        G4R_CUDA_OK(cudaEventRecord(ctx->ev, s));
+        ctx->pending = true;
+        ctx->renders_since_project = 0;
+    }
     return G4R_OK;
 }
 
@@ -172,7 +174,6 @@ int64_t g4r_wait_num_rendered(G4RContext* ctx) {
 int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g, void* geom, void* img, void* binning,
                        int64_t capacity, const G4RForwardOut* out, void* stream) {
     int rc;
-    if (!ctx) return g4r_set_error(G4R_EINVAL, "context is NULL");
     if ((rc = check_frame(f, false)) != G4R_OK) return rc;
     if (!g || g->P < 0) return g4r_set_error(G4R_EINVAL, "gaussians is NULL or P is negative");   // phase 2 only needs P
     if (!out || !out->color || !out->depth || !out->opacity) return g4r_set_error(G4R_EINVAL, "output images are NULL");
@@ -182,14 +183,14 @@ int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g
     if (((uintptr_t)geom | (uintptr_t)img | (uintptr_t)binning) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     if (g->P > 0) {
-        if (ctx->renders_since_project > 0) {
+        if (ctx && ctx->renders_since_project > 0) {
             // re-run after a capacity overflow: the aborted attempt touched nothing (every phase-2 kernel
             // exits when N > capacity), but be robust to a caller re-rendering a completed frame too.
             const ImageLayout il(f->width, f->height);
             G4R_CUDA_OK(cudaMemsetAsync((char*)img + il.counts, 0, il.ranges - il.counts, s));
             G4R_CUDA_OK(cudaMemsetAsync(out->n_touched, 0, sizeof(int32_t) * (size_t)g->P, s));
         }
-        ctx->renders_since_project++;
+        if (ctx) ctx->renders_since_project++;
         if ((rc = launch_scatter_sort(*f, g->P, out->radii, geom, img, binning, capacity, s)) != G4R_OK) return rc;
     }
     return launch_composite_forward(*f, g->P, geom, img, binning, capacity, *out, s);

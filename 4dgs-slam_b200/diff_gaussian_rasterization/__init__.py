@@ -31,6 +31,8 @@ __all__ = [
     "GaussianRasterizer",
     "rasterize_gaussians",
     "rasterize_gaussians_with_state",
+    "captured_overflow",
+    "reset_captured",
 ]
 
 # ----------------------------------------------------------------------------------------------
@@ -162,6 +164,25 @@ def _context(device: torch.device) -> int:
 # instance-capacity hint per device: high-water mark of num_rendered with slow decay
 _cap_hint: dict = {}
 
+# CUDA-graph capture: capacity = hint x this factor; (image state, capacity, header offset) of every captured forward
+_GRAPH_CAPACITY_FACTOR = 2.0
+_captured: list = []
+
+
+def captured_overflow() -> bool:
+    """True if, in the most recent replay, any forward captured in a CUDA graph produced more (tile, Gaussian) instances
+    than the capacity fixed at capture time (its outputs are then stale).  Synchronises the device; call it as often
+    as the application needs the guarantee, then re-capture after more eager warm-up iterations."""
+    bad = False
+    for img, cap, off in _captured:
+        n = int(img[off:off + 4].view(torch.int32).item()) & 0xffffffff
+        bad = bad or n > cap
+    return bad
+
+
+def reset_captured() -> None:
+    _captured.clear()
+
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None or t.numel() == 0:
@@ -253,6 +274,21 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         frame = _make_frame(rs, device, M, keep)
         g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
         out = _ForwardOut(color.data_ptr(), depth.data_ptr(), opacity.data_ptr(), radii.data_ptr(), n_touched.data_ptr())
+
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture (torch.cuda.graph around forward + loss + backward): no host read-back is possible, so
+            # phase 2 gets a generous fixed capacity derived from the eager warm-up iterations.  Replays whose instance
+            # count outgrows it leave the outputs untouched; `captured_overflow()` reports that after a replay.
+            key = (device.index, W, H)
+            cap = int(max(_cap_hint.get(key, 0), 4 * P) * _GRAPH_CAPACITY_FACTOR) + 4096
+            binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
+            _check(_lib.g4r_forward_project(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
+                                            radii.data_ptr(), n_touched.data_ptr(), stream))
+            _check(_lib.g4r_forward_render(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
+                                           binning.data_ptr(), cap, ctypes.byref(out), stream))
+            _captured.append((img, cap, _layout(P, W, H, cap).img_header))
+            state = dict(P=P, N=-1, geom=geom, img=img, binning=binning, capacity=cap)
+            return color, radii, depth, opacity, n_touched, state
 
         _check(_lib.g4r_forward_project(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                         radii.data_ptr(), n_touched.data_ptr(), stream))
@@ -387,8 +423,11 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
+_EMPTY = torch.Tensor([])
+
+
 def _empty() -> torch.Tensor:
-    return torch.Tensor([])
+    return _EMPTY
 
 
 class GaussianRasterizer(nn.Module):

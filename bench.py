@@ -231,6 +231,54 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
     return e0.elapsed_time(e1)
 
 
+def run_cuda_graph(dgr, wl: Workload, steps, flush):
+    """fwd + loss + bwd captured once in a CUDA graph and replayed (possible because this rasterizer never blocks the host;
+    the reference's forward does a blocking cudaMemcpy and cannot be captured).  Returns per-replay milliseconds."""
+    sc, dev = wl.dev, wl.device
+    rs = dgr.GaussianRasterizationSettings(image_height=sc.H, image_width=sc.W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=sc.bg,
+                                           scale_modifier=sc.scale_modifier, viewmatrix=sc.viewmatrix, projmatrix=sc.projmatrix,
+                                           projmatrix_raw=sc.projmatrix_raw, sh_degree=sc.sh_degree, campos=sc.campos, prefiltered=False, debug=False)
+    keys = [k for k in ("means3D", "opacities", "shs", "scales", "rotations") if getattr(sc, k) is not None]
+    leaf = {k: getattr(sc, k).detach().clone().requires_grad_(True) for k in keys}
+
+    def step():
+        m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
+        theta = torch.zeros(3, device=dev, requires_grad=True)
+        rho = torch.zeros(3, device=dev, requires_grad=True)
+        color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
+            means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf.get("shs"), colors_precomp=sc.colors_precomp,
+            scales=leaf.get("scales"), rotations=leaf.get("rotations"), cov3D_precomp=sc.cov3D_precomp, theta=theta, rho=rho)
+        loss = (color * wl.grad_color).sum() + (depth * wl.grad_depth).sum()
+        return torch.autograd.grad(loss, list(leaf.values()) + [m2d, theta, rho])
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    dgr.reset_captured()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    for _ in range(3):
+        graph.replay()
+        flush()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record()
+        graph.replay()
+        b.record()
+        flush()
+    torch.cuda.synchronize()
+    overflow = dgr.captured_overflow()
+    dgr.reset_captured()
+    del out
+    return [a.elapsed_time(b) for a, b in ev], overflow
+
+
 def timed_steps(step, steps, warmup, flush, dist_barrier, sampler=None):
     """W warm-ups, then K steps each bracketed by CUDA events on the current stream; L2 is flushed (outside the timed
     region) between steps.  Returns per-step milliseconds."""
@@ -359,6 +407,14 @@ def main():
         dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
     e2e_value = world * K2 / (float(t_h.item()) / 1000.0)
 
+    graph_ms, graph_overflow = (None, None)
+    if lib is not None and rank == 0 and not use_dist:
+        try:
+            gms, graph_overflow = run_cuda_graph(dgr, wl, args.steps, flush)
+            graph_ms = sum(gms) / len(gms)
+        except Exception as exc:                      # the eager numbers stand on their own
+            sys.stderr.write(f"cuda-graph leg skipped: {exc!r}\n")
+
     if rank == 0:
         sc = wl.cpu
         # workload statistics for the roofline: N from one extra forward
@@ -415,6 +471,10 @@ def main():
                                 "traffic": traffic, "algorithmic_bytes_per_launch": per_kernel[dom], "ms_per_launch": kt[dom],
                                 "peak_source": peak_src}
             line["kernel_ms"] = {k: round(v[0], 5) for k, v in stage.items()}
+        if graph_ms is not None:
+            line["cuda_graph"] = {"value": 1000.0 / graph_ms, "unit": "frames/s", "ms_per_step": graph_ms, "capacity_overflow": graph_overflow,
+                                  "note": "same step (fwd + loss + bwd through the public API) captured once with torch.cuda.graph and replayed; "
+                                          "informational -- `value` above is the eager number"}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))

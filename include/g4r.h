@@ -130,7 +130,8 @@ size_t g4r_backward_scratch_bytes(int32_t P);         /* per-Gaussian gradient a
  * Enqueues: per-Gaussian projection (writes radii, zeroes n_touched, fills geom), per-tile instance
  * counts and their exclusive scan (writes ranges into img), then an async copy of the
  * instance total N into the context's pinned int and an event record.
- * Never blocks. */
+ * Never blocks.  ctx may be NULL: nothing is read back (CUDA-graph capture; the caller guarantees phase 2's capacity and
+ * can read N later from the image state, G4RLayout.img_header). */
 int g4r_forward_project(G4RContext* ctx, const G4RFrame* frame, const G4RGaussians* g,
                         void* geom, void* img, int32_t* radii, int32_t* n_touched, void* stream);
 

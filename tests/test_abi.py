@@ -58,7 +58,7 @@ def test_bad_arguments_are_reported_not_crashed():
     lib = ctypes.CDLL(LIB)
     lib.g4r_last_error.restype = ctypes.c_char_p
     rc = lib.g4r_forward_project(None, None, None, None, None, None, None, None)
-    assert rc == -1 and b"context" in lib.g4r_last_error()
+    assert rc == -1 and b"frame" in lib.g4r_last_error()
     rc = lib.g4r_backward(None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"frame" in lib.g4r_last_error()
     lib.g4r_mark_visible.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 5

@@ -307,3 +307,44 @@ def test_sharded_render_two_gpus(tmp_path):
            "--master-port", "29533", os.path.join(ROOT, "tools", "sharded_check.py"), "--workload", "small", "--iters", "2", "--out", str(tmp_path)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "SHARDED CHECK PASS" in r.stdout, r.stdout[-3000:]
+
+
+def test_cuda_graph_capture_matches_eager(device):
+    """forward + loss + backward captured once in a CUDA graph (no host sync anywhere on the path) and replayed: same image
+    bits as eager, gradients equal up to atomics order.  The reference cannot be captured (blocking cudaMemcpy in forward)."""
+    import diff_gaussian_rasterization as dgr
+    sc = make_scene(20000, 320, 240, sh_degree=0, seed=95).to(device)
+    rs = runners.settings_for(sc, dgr)
+    leaf = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+
+    def step():
+        m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
+        theta = torch.zeros(3, device=device, requires_grad=True)
+        rho = torch.zeros(3, device=device, requires_grad=True)
+        color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
+            means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf["shs"], scales=leaf["scales"],
+            rotations=leaf["rotations"], theta=theta, rho=rho)
+        loss = (color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()
+        grads = torch.autograd.grad(loss, [leaf["means3D"], leaf["scales"], leaf["rotations"], leaf["opacities"], leaf["shs"], m2d, theta, rho])
+        return color, depth, radii, n_touched, grads
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager = step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    dgr.reset_captured()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert not dgr.captured_overflow()
+    for a, b in zip(out[:4], eager[:4]):
+        assert torch.equal(a, b)
+    for a, b in zip(out[4], eager[4]):
+        assert float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)) < 1e-4
+    dgr.reset_captured()
