@@ -39,6 +39,41 @@ def timeit(fn, warmup=3, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+def graph_ms(sc, dgr, iters=10):
+    """fwd + loss + bwd of the public API captured in a CUDA graph; per-replay milliseconds."""
+    dev = sc.means3D.device
+    rs = runners.settings_for(sc, dgr)
+    keys = [k for k in ("means3D", "opacities", "shs", "scales", "rotations") if getattr(sc, k) is not None]
+    leaf = {k: getattr(sc, k).detach().clone().requires_grad_(True) for k in keys}
+
+    def step():
+        m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
+        theta = torch.zeros(3, device=dev, requires_grad=True)
+        rho = torch.zeros(3, device=dev, requires_grad=True)
+        color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
+            means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf.get("shs"), colors_precomp=sc.colors_precomp,
+            scales=leaf.get("scales"), rotations=leaf.get("rotations"), cov3D_precomp=sc.cov3D_precomp, theta=theta, rho=rho)
+        loss = (color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()
+        return torch.autograd.grad(loss, list(leaf.values()) + [m2d, theta, rho])
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    dgr.reset_captured()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()
+    ms = timeit(g.replay, warmup=3, iters=iters)
+    ok = not dgr.captured_overflow()
+    dgr.reset_captured()
+    del out
+    return ms, ok
+
+
 def main():
     dev = torch.device("cuda:0")
     import diff_gaussian_rasterization as dgr
@@ -57,6 +92,10 @@ def main():
         mine = runners.run_g4r(sc, want_grads=False)
         row = {"P": sc.P, "N": int(mine["num_rendered"]), "max_tile": int((mine["ranges"][:, 1] - mine["ranges"][:, 0]).max())}
         row["ours_ms"] = timeit(lambda: runners.run_public_api(sc, dgr))
+        try:
+            row["ours_cuda_graph_ms"], row["graph_capacity_ok"] = graph_ms(sc, dgr)
+        except Exception as exc:
+            row["ours_cuda_graph_ms"] = f"failed: {exc!r}"[:200]
         if ref is not None:
             r = refload.run_reference(sc, want_grads=False)
             row["ints_equal"] = bool(torch.equal(mine["point_list"], r["point_list"]) and torch.equal(mine["radii"], r["radii"])
