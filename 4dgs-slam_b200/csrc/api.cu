@@ -88,7 +88,7 @@ static int check_gaussians(const G4RFrame* f, const G4RGaussians* g) {
 extern "C" {
 
 const char* g4r_last_error(void) { return g_err; }
-int g4r_version(void) { return 2; }
+int g4r_version(void) { return 3; }
 void g4r_struct_sizes(int32_t* out5) {
     out5[0] = (int32_t)sizeof(G4RFrame); out5[1] = (int32_t)sizeof(G4RGaussians); out5[2] = (int32_t)sizeof(G4RForwardOut);
     out5[3] = (int32_t)sizeof(G4RBackwardIO); out5[4] = (int32_t)sizeof(G4RLayout);
@@ -238,6 +238,15 @@ int g4r_backward(const G4RFrame* f, const G4RGaussians* g, const int32_t* radii,
         if ((rc = g4r_backward_composite(f, g->P, geom, img, binning, io->dL_dcolor, io->dL_ddepth, scratch, stream)) != G4R_OK) return rc;
     }
     return g4r_backward_gaussians(f, g, radii, geom, scratch, io, stream);
+}
+
+int g4r_tile_rows(const G4RFrame* f, int32_t P, const int32_t* radii, const void* geom, int32_t* rows, void* stream) {
+    int rc;
+    if ((rc = check_frame(f, false)) != G4R_OK) return rc;
+    if (P <= 0) return G4R_OK;
+    if (!radii || !geom || !rows) return g4r_set_error(G4R_EINVAL, "radii/geom/rows are NULL");
+    if (((uintptr_t)geom & 15u) || ((uintptr_t)rows & 7u)) return g4r_set_error(G4R_EINVAL, "geom must be 16-byte and rows 8-byte aligned");
+    return launch_tile_rows(*f, P, radii, geom, rows, (cudaStream_t)stream);
 }
 
 int g4r_project_only(const G4RFrame* f, const G4RGaussians* g, void* geom, int32_t* radii, int32_t* n_touched, void* stream) {

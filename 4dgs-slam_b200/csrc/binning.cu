@@ -77,8 +77,7 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
 __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
                                                             const uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
                                                             uint2* __restrict__ pairs, const uint32_t* __restrict__ header,
-                                                            uint32_t capacity, uint32_t gx, uint32_t gy, uint32_t tile_rank,
-                                                            uint32_t tile_world) {
+                                                            uint32_t capacity, uint32_t gx, uint32_t gy, TileOwner own) {
     if (header[0] > capacity) return;           // uniform: caller re-runs phase 2 with a larger buffer
     const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
     if (i >= P) return;
@@ -91,7 +90,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
     for (uint32_t ty = r.y0; ty < r.y1; ++ty)
         for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
             const uint32_t t = ty * gx + tx;
-            if (tile_world > 1 && t % tile_world != tile_rank) continue;        // not this rank's tile
+            if (!own.owns(t, gx)) continue;                                      // not this rank's tile
             const uint32_t slot = __ldg(&ranges[t].x) + atomicAdd(cursors + (size_t)t * G4R_COUNT_STRIDE, 1u);   // cursors start at 0
             pairs[slot] = make_uint2(key, (uint32_t)i);
         }
@@ -100,8 +99,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
 // Sharded render: per-owned-tile histogram over the all-gathered records (project_kernel's fused histogram only sees
 // the local shard).
 __global__ void __launch_bounds__(G4R_BLOCK) count_tiles_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
-                                                                uint32_t* __restrict__ counts, uint32_t gx, uint32_t gy,
-                                                                uint32_t tile_rank, uint32_t tile_world) {
+                                                                uint32_t* __restrict__ counts, uint32_t gx, uint32_t gy, TileOwner own) {
     const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
     if (i >= P) return;
     const int radius = radii[i];
@@ -111,7 +109,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) count_tiles_kernel(int P, const int
     for (uint32_t ty = r.y0; ty < r.y1; ++ty)
         for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
             const uint32_t t = ty * gx + tx;
-            if (t % tile_world == tile_rank) atomicAdd(counts + (size_t)t * G4R_COUNT_STRIDE, 1u);
+            if (own.owns(t, gx)) atomicAdd(counts + (size_t)t * G4R_COUNT_STRIDE, 1u);
         }
 }
 
@@ -120,8 +118,32 @@ int launch_count_tiles(const G4RFrame& f, int P, const int32_t* radii, const voi
     const ImageLayout il(f.width, f.height);
     count_tiles_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(
         P, radii, (const float4*)((const char*)geom + gl.rec), (uint32_t*)((char*)img + il.counts), (uint32_t)il.tiles_x,
-        (uint32_t)il.tiles_y, g4r_tile_rank(f), g4r_tile_world(f));
+        (uint32_t)il.tiles_y, g4r_owner(f));
     G4R_LAUNCH_OK("count_tiles_kernel");
+    return G4R_OK;
+}
+
+// First / last tile row of every Gaussian's rectangle: destinations of the all-to-all exchange of the sharded render.
+__global__ void __launch_bounds__(G4R_BLOCK) tile_rows_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
+                                                              int32_t* __restrict__ rows, uint32_t gx, uint32_t gy) {
+    const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
+    if (i >= P) return;
+    const int radius = radii[i];
+    int2 r = make_int2(1, 0);
+    if (radius > 0) {
+        const float4 a = ldg4(rec + (size_t)i * 3);
+        const TileRect t = tile_rect(a.x, a.y, radius, gx, gy);
+        if (t.x1 > t.x0 && t.y1 > t.y0) r = make_int2((int)t.y0, (int)t.y1 - 1);
+    }
+    reinterpret_cast<int2*>(rows)[i] = r;
+}
+
+int launch_tile_rows(const G4RFrame& f, int P, const int32_t* radii, const void* geom, int32_t* rows, cudaStream_t s) {
+    const GeomLayout gl(P);
+    const ImageLayout il(f.width, f.height);
+    tile_rows_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, (const float4*)((const char*)geom + gl.rec), rows,
+                                                                          (uint32_t)il.tiles_x, (uint32_t)il.tiles_y);
+    G4R_LAUNCH_OK("tile_rows_kernel");
     return G4R_OK;
 }
 
@@ -348,7 +370,7 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
     scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
                                                                          (uint32_t*)(ib + il.counts), (uint2*)(bb + bl.pairs),
                                                                          (const uint32_t*)(ib + il.header), cap, (uint32_t)il.tiles_x,
-                                                                         (uint32_t)il.tiles_y, g4r_tile_rank(f), g4r_tile_world(f));
+                                                                         (uint32_t)il.tiles_y, g4r_owner(f));
     g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");
     g4r_stage_begin(ST_TILE_SORT, s);

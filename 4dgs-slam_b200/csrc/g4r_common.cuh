@@ -117,8 +117,24 @@ enum G4RStage { ST_PROJECT = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_COMPO
 void g4r_stage_begin(int stage, cudaStream_t s);
 void g4r_stage_end(int stage, cudaStream_t s);
 
-static inline uint32_t g4r_tile_world(const G4RFrame& f) { return f.tile_world > 0 ? (uint32_t)f.tile_world : 1u; }
-static inline uint32_t g4r_tile_rank(const G4RFrame& f) { return f.tile_world > 0 ? (uint32_t)f.tile_rank : 0u; }
+// Tile ownership of the sharded render: interleaved (t % world == rank) or a contiguous strip of tile rows.
+struct TileOwner {
+    uint32_t rank, world, row_begin, row_end;      // world > 1: modulo; else row_end > row_begin: strip; else everything
+    __host__ __device__ __forceinline__ bool all() const { return world <= 1u && row_end <= row_begin; }
+    __host__ __device__ __forceinline__ bool owns(uint32_t tile, uint32_t gx) const {
+        if (world > 1u) return tile % world == rank;
+        if (row_end > row_begin) { const uint32_t ty = tile / gx; return ty >= row_begin && ty < row_end; }
+        return true;
+    }
+};
+static inline TileOwner g4r_owner(const G4RFrame& f) {
+    TileOwner o;
+    o.world = f.tile_world > 0 ? (uint32_t)f.tile_world : 1u;
+    o.rank = f.tile_world > 0 ? (uint32_t)f.tile_rank : 0u;
+    o.row_begin = f.tile_row_begin > 0 ? (uint32_t)f.tile_row_begin : 0u;
+    o.row_end = f.tile_row_end > 0 ? (uint32_t)f.tile_row_end : 0u;
+    return o;
+}
 
 // ---- kernel launchers (one translation unit each) ----------------------------------------
 int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* img, int32_t* radii, int32_t* n_touched,
@@ -126,6 +142,7 @@ int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* i
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s);
 int launch_count_tiles(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, cudaStream_t s);
+int launch_tile_rows(const G4RFrame& f, int P, const int32_t* radii, const void* geom, int32_t* rows, cudaStream_t s);
 int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
                         int64_t capacity, cudaStream_t s);
 int launch_composite_forward(const G4RFrame& f, int P, const void* geom, void* img, const void* binning, int64_t capacity,

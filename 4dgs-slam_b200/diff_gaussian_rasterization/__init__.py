@@ -50,6 +50,7 @@ class _Frame(ctypes.Structure):
         ("bg", ctypes.c_void_p), ("viewmatrix", ctypes.c_void_p), ("projmatrix", ctypes.c_void_p),
         ("projmatrix_raw", ctypes.c_void_p), ("campos", ctypes.c_void_p),
         ("tile_rank", ctypes.c_int32), ("tile_world", ctypes.c_int32),
+        ("tile_row_begin", ctypes.c_int32), ("tile_row_end", ctypes.c_int32),
     ]
 
 
@@ -130,8 +131,8 @@ def _load_library() -> ctypes.CDLL:
     if list(sizes) != mine:
         raise ImportError(f"diff_gaussian_rasterization: struct layout mismatch between libg4r.so {list(sizes)} and the Python "
                           f"bindings {mine}; rebuild the library")
-    if lib.g4r_version() != 2:
-        raise ImportError(f"diff_gaussian_rasterization: libg4r.so has ABI version {lib.g4r_version()}, expected 2; rebuild it")
+    if lib.g4r_version() != 3:
+        raise ImportError(f"diff_gaussian_rasterization: libg4r.so has ABI version {lib.g4r_version()}, expected 3; rebuild it")
     return lib
 
 
@@ -211,6 +212,7 @@ def _make_frame(rs: "GaussianRasterizationSettings", device: torch.device, sh_co
     f.bg, f.viewmatrix, f.projmatrix = mat(rs.bg), mat(rs.viewmatrix), mat(rs.projmatrix)
     f.projmatrix_raw, f.campos = mat(rs.projmatrix_raw), mat(rs.campos)
     f.tile_rank, f.tile_world = 0, 1
+    f.tile_row_begin, f.tile_row_end = 0, 0
     return f
 
 

@@ -15,7 +15,13 @@ backward  5. composite backward of the owned tiles -> partial accumulators for A
 
 Global Gaussian ids are ``rank * Pmax + local index`` (shards padded to the largest one), which preserves the order of
 the concatenated cloud, so every tile's sorted list -- and therefore every pixel -- is identical to the single-GPU
-result.  The kernel calls go through a *backend* object so that the host logic (sharding, collectives, padding) can be
+result.
+
+``exchange="alltoall"`` (default) replaces steps 2 and 6 by variable-size all-to-alls: rank r owns a contiguous strip of tile
+rows, every splat record travels only to the ranks whose strip its tile rectangle touches (~1.3 ranks instead of all),
+and the accumulator rows travel back the same way and are scatter-added at the owner.  Records arrive ordered by
+(source rank, local index) = global id order, so ties in depth still resolve like on one GPU.  ``exchange="allgather"``
+is the simpler variant described above (interleaved tile ownership).  The kernel calls go through a *backend* object so that the host logic (sharding, collectives, padding) can be
 exercised with the gloo backend on CPU by the tests, which inject a CPU backend; the product default is the CUDA library
 and there is no fallback.
 """
@@ -30,7 +36,7 @@ import torch.distributed as dist
 from . import (_BackwardIO, _ForwardOut, _check, _context, _dev_f32, _lib, _make_frame, _make_gaussians, _ptr,
                GaussianRasterizationSettings)
 
-__all__ = ["ShardedGaussianRasterizer", "shard_bounds", "owned_tiles"]
+__all__ = ["ShardedGaussianRasterizer", "shard_bounds", "owned_tiles", "strip_bounds"]
 
 
 def shard_bounds(P: int, world: int, rank: int):
@@ -46,27 +52,45 @@ def owned_tiles(W: int, H: int, world: int, rank: int) -> torch.Tensor:
     return (torch.arange(tiles) % world) == rank
 
 
-class CudaBackend:
-    """The five kernel groups of the sharded render on the current CUDA device (C ABI of include/g4r.h)."""
+def _set_owner(frame, owner) -> None:
+    """owner = ("mod", rank, world) | ("rows", row_begin, row_end)"""
+    frame.tile_rank, frame.tile_world, frame.tile_row_begin, frame.tile_row_end = 0, 1, 0, 0
+    if owner[0] == "mod":
+        frame.tile_rank, frame.tile_world = int(owner[1]), int(owner[2])
+    else:
+        frame.tile_row_begin, frame.tile_row_end = int(owner[1]), int(owner[2])
 
-    def project(self, rs, M, tile_rank, tile_world, means3D, opacities, sh, colors, scales, rots, cov, rec, radii, n_touched):
+
+class CudaBackend:
+    """The kernel groups of the sharded render on the current CUDA device (C ABI of include/g4r.h)."""
+
+    def tile_rows(self, rs, P, radii, geom):
+        dev = radii.device
+        rows = torch.empty((max(P, 1), 2), dtype=torch.int32, device=dev)
+        keep = []
+        with torch.cuda.device(dev):
+            frame = _make_frame(rs, dev, 0, keep)
+            _check(_lib.g4r_tile_rows(ctypes.byref(frame), P, radii.data_ptr(), geom.data_ptr(), rows.data_ptr(),
+                                      torch.cuda.current_stream(dev).cuda_stream))
+        return rows[:P]
+
+    def project(self, rs, M, means3D, opacities, sh, colors, scales, rots, cov, rec, radii, n_touched):
         dev = means3D.device
         keep = []
         with torch.cuda.device(dev):
             frame = _make_frame(rs, dev, M, keep)
-            frame.tile_rank, frame.tile_world = tile_rank, tile_world
             g = _make_gaussians(int(means3D.shape[0]), means3D, opacities, sh, colors, scales, rots, cov)
             _check(_lib.g4r_project_only(ctypes.byref(frame), ctypes.byref(g), rec.data_ptr(), radii.data_ptr(), n_touched.data_ptr(),
                                          torch.cuda.current_stream(dev).cuda_stream))
 
-    def render(self, rs, tile_rank, tile_world, P_all, rec_all, radii_all, n_touched_all, images, img_state, cap_hint):
+    def render(self, rs, owner, P_all, rec_all, radii_all, n_touched_all, images, img_state, cap_hint):
         dev = rec_all.device
         keep = []
         with torch.cuda.device(dev):
             ctx = _context(dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             frame = _make_frame(rs, dev, 0, keep)
-            frame.tile_rank, frame.tile_world = tile_rank, tile_world
+            _set_owner(frame, owner)
             g = _make_gaussians(P_all, rec_all, rec_all, None, None, None, None, None)
             _check(_lib.g4r_count_tiles(ctx, ctypes.byref(frame), P_all, radii_all.data_ptr(), rec_all.data_ptr(), img_state.data_ptr(), stream))
             out = _ForwardOut(images[0:3].data_ptr(), images[3:4].data_ptr(), images[4:5].data_ptr(), radii_all.data_ptr(),
@@ -85,12 +109,12 @@ class CudaBackend:
                                                binning.data_ptr(), cap, ctypes.byref(out), stream))
         return binning, N
 
-    def composite_backward(self, rs, tile_rank, tile_world, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):
+    def composite_backward(self, rs, owner, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):
         dev = rec_all.device
         keep = []
         with torch.cuda.device(dev):
             frame = _make_frame(rs, dev, 0, keep)
-            frame.tile_rank, frame.tile_world = tile_rank, tile_world
+            _set_owner(frame, owner)
             _check(_lib.g4r_backward_composite(ctypes.byref(frame), P_all, rec_all.data_ptr(), img_state.data_ptr(), binning.data_ptr(),
                                                grad_color.data_ptr(), grad_depth.data_ptr(), acc_all.data_ptr(),
                                                torch.cuda.current_stream(dev).cuda_stream))
@@ -114,6 +138,8 @@ class CudaBackend:
         return _lib.g4r_geom_bytes(P)
 
 
+_lib.g4r_tile_rows.restype = ctypes.c_int
+_lib.g4r_tile_rows.argtypes = [ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 4
 _lib.g4r_project_only.restype = ctypes.c_int
 _lib.g4r_project_only.argtypes = [ctypes.c_void_p] * 6
 _lib.g4r_count_tiles.restype = ctypes.c_int
@@ -171,8 +197,8 @@ class _ShardedRasterize(torch.autograd.Function):
         # local geometry state: records first (the all-gathered slab), the per-Gaussian clamp bytes behind them
         geom_local = torch.zeros((max(Pmax * 48, backend.geom_state_bytes(max(P, 1))) + 256,), dtype=torch.uint8, device=dev)
         if P > 0:
-            backend.project(rs, M, rank, world, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, geom_local,
-                            radii_local, ntouch_local)
+            backend.project(rs, M, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, geom_local, radii_local,
+                            ntouch_local)
         rec_local = geom_local[: Pmax * 48].view(torch.float32).view(Pmax, REC_FLOATS)
 
         # 2. all-gather records and radii
@@ -186,7 +212,7 @@ class _ShardedRasterize(torch.autograd.Function):
         ntouch_all = torch.zeros((P_all,), **i32)
         img_state = torch.empty((backend.image_state_bytes(W, H),), dtype=torch.uint8, device=dev)
         cap = max(4096, int(1.5 * 4 * P_all / world))
-        binning, N = backend.render(rs, rank, world, P_all, rec_all, radii_all, ntouch_all, images, img_state, cap)
+        binning, N = backend.render(rs, ("mod", rank, world), P_all, rec_all, radii_all, ntouch_all, images, img_state, cap)
 
         # 4. image all-reduce, n_touched reduce-scatter
         dist.all_reduce(images, op=dist.ReduceOp.SUM, group=group)
@@ -216,11 +242,141 @@ class _ShardedRasterize(torch.autograd.Function):
 
         # 5. + 6. partial accumulators of the owned tiles -> owners of the Gaussians
         acc_all = torch.empty((P_all, ACC_FLOATS), **f32)
-        backend.composite_backward(rs, rank, world, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all)
+        backend.composite_backward(rs, ("mod", rank, world), P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all)
         acc_local = torch.empty((Pmax, ACC_FLOATS), **f32)
         _reduce_scatter_sum(acc_local, acc_all, group)
 
         # 7. per-Gaussian backward of the local shard
+        grads = dict(means3D=torch.empty((P, 3), **f32), means2D=torch.empty((P, 3), **f32), opacities=torch.empty(ctx.opacities_shape, **f32))
+        if sh.numel():
+            grads["sh"] = torch.empty((P, M, 3), **f32)
+        if colors_precomp.numel():
+            grads["colors"] = torch.empty((P, 3), **f32)
+        if scales.numel():
+            grads["scales"] = torch.empty((P, 3), **f32)
+            grads["rots"] = torch.empty((P, 4), **f32)
+        if cov3Ds_precomp.numel():
+            grads["cov"] = torch.empty((P, 6), **f32)
+        tau = torch.zeros((8,), **f32)
+        if P > 0:
+            backend.gaussian_backward(rs, M, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local,
+                                      acc_local, grads, tau)
+        dist.all_reduce(tau, op=dist.ReduceOp.SUM, group=group)
+        needs = ctx.needs_input_grad
+        return (grads["means3D"], grads["means2D"], grads.get("sh"), grads.get("colors"), grads["opacities"], grads.get("scales"),
+                grads.get("rots"), grads.get("cov"), tau[3:6].view(1, -1) if needs[8] else None, tau[:3].view(1, -1) if needs[9] else None,
+                None, None, None)
+
+
+def strip_bounds(tiles_y: int, world: int, rank: int):
+    """Contiguous strip of tile rows [begin, end) owned by `rank`."""
+    return (rank * tiles_y) // world, ((rank + 1) * tiles_y) // world
+
+
+def _all_to_all_rows(send: torch.Tensor, send_counts, recv_counts, group) -> torch.Tensor:
+    """Variable-size all-to-all of the rows of a 2-D tensor."""
+    recv = torch.empty((int(sum(recv_counts)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
+                           input_split_sizes=[int(c) for c in send_counts], group=group)
+    return recv
+
+
+class _ShardedRasterizeA2A(torch.autograd.Function):
+    """Strip ownership + variable-size all-to-all of splat records (forward) and accumulator rows (backward)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs, group, backend):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = means3D.device
+        H, W = int(rs.image_height), int(rs.image_width)
+        tiles_y = (H + 15) // 16
+        P = int(means3D.shape[0])
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        means3D = _dev_f32(means3D, dev)
+        opacities = _dev_f32(opacities, dev)
+        sh = _dev_f32(sh, dev) if sh.numel() else sh
+        colors_precomp = _dev_f32(colors_precomp, dev) if colors_precomp.numel() else colors_precomp
+        scales = _dev_f32(scales, dev) if scales.numel() else scales
+        rotations = _dev_f32(rotations, dev) if rotations.numel() else rotations
+        cov3Ds_precomp = _dev_f32(cov3Ds_precomp, dev) if cov3Ds_precomp.numel() else cov3Ds_precomp
+        M = int(sh.size(1)) if sh.numel() else 0
+
+        # 1. local projection
+        Pp = max(P, 1)
+        geom_local = torch.zeros((max(Pp * 48, backend.geom_state_bytes(Pp)) + 256,), dtype=torch.uint8, device=dev)
+        radii_local = torch.zeros((Pp,), **i32)
+        ntouch_local = torch.zeros((Pp,), **i32)
+        if P > 0:
+            backend.project(rs, M, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, geom_local, radii_local,
+                            ntouch_local)
+        rec_local = geom_local[: Pp * 48].view(torch.float32).view(Pp, REC_FLOATS)
+
+        # 2. destinations: every rank whose strip of tile rows intersects the splat's rectangle
+        rows = backend.tile_rows(rs, P, radii_local, geom_local) if P > 0 else torch.zeros((0, 2), **i32)
+        begins = torch.tensor([strip_bounds(tiles_y, world, r)[0] for r in range(world)], **i32).view(world, 1)
+        ends = torch.tensor([strip_bounds(tiles_y, world, r)[1] for r in range(world)], **i32).view(world, 1)
+        first, last = rows[:, 0].view(1, -1), rows[:, 1].view(1, -1)
+        touch = (first < ends) & (last >= begins) & (last >= first)                  # (world, P)
+        dest_src = torch.nonzero(touch)                                              # sorted by destination, then local index
+        send_idx = dest_src[:, 1].contiguous()
+        send_counts = touch.sum(dim=1).to(torch.int64)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        send_counts_l, recv_counts_l = send_counts.tolist(), recv_counts.tolist()
+
+        # 3. exchange the 48-byte records; the radius rides in the record's spare slot
+        send_rec = rec_local[send_idx].clone()
+        send_rec[:, 11] = radii_local[send_idx].view(torch.float32) if send_idx.numel() else send_rec[:, 11]
+        rec_recv = _all_to_all_rows(send_rec, send_counts_l, recv_counts_l, group)
+        P_recv = int(rec_recv.shape[0])
+        rec_work = rec_recv if P_recv > 0 else torch.zeros((1, REC_FLOATS), **f32)
+        radii_recv = rec_work[:, 11].contiguous().view(torch.int32)
+
+        # 4. owned strip: count / scan / scatter / sort / composite over the received records
+        rb, re_ = strip_bounds(tiles_y, world, rank)
+        images = torch.zeros((5, H, W), **f32)
+        ntouch_recv = torch.zeros((max(P_recv, 1),), **i32)
+        img_state = torch.empty((backend.image_state_bytes(W, H),), dtype=torch.uint8, device=dev)
+        cap = max(4096, int(6 * max(P_recv, 1)))
+        binning, N = backend.render(rs, ("rows", rb, re_), P_recv, rec_work, radii_recv, ntouch_recv, images, img_state, cap)
+
+        # 5. image all-reduce (every pixel has exactly one owner), n_touched back to the owners of the Gaussians
+        dist.all_reduce(images, op=dist.ReduceOp.SUM, group=group)
+        ntouch_back = _all_to_all_rows(ntouch_recv[:P_recv].view(-1, 1), recv_counts_l, send_counts_l, group).view(-1)
+        if send_idx.numel():
+            ntouch_local.index_add_(0, send_idx, ntouch_back)
+
+        ctx.rs, ctx.group, ctx.backend, ctx.P, ctx.M, ctx.P_recv = rs, group, backend, P, M, P_recv
+        ctx.counts = (send_counts_l, recv_counts_l)
+        ctx.owner = ("rows", rb, re_)
+        ctx.opacities_shape = tuple(opacities.shape)
+        ctx.binning = binning
+        ctx.save_for_backward(means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, rec_work, img_state, send_idx)
+        radii = radii_local[:P].clone()
+        n_touched = ntouch_local[:P].clone()
+        ctx.mark_non_differentiable(radii, n_touched)
+        return images[0:3].clone(), radii, images[3:4].clone(), images[4:5].clone(), n_touched
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_opacity, grad_ntouched):
+        means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, rec_work, img_state, send_idx = ctx.saved_tensors
+        rs, group, backend, P, M, P_recv = ctx.rs, ctx.group, ctx.backend, ctx.P, ctx.M, ctx.P_recv
+        send_counts_l, recv_counts_l = ctx.counts
+        dev = means3D.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        grad_color = _dev_f32(grad_color, dev)
+        grad_depth = _dev_f32(grad_depth, dev)
+
+        # composite backward of the owned strip -> one accumulator row per received record -> back to the owners
+        acc_recv = torch.zeros((max(P_recv, 1), ACC_FLOATS), **f32)
+        if P_recv > 0:
+            backend.composite_backward(rs, ctx.owner, P_recv, rec_work, img_state, ctx.binning, grad_color, grad_depth, acc_recv)
+        acc_back = _all_to_all_rows(acc_recv[:P_recv], recv_counts_l, send_counts_l, group)
+        acc_local = torch.zeros((max(P, 1), ACC_FLOATS), **f32)
+        if send_idx.numel():
+            acc_local.index_add_(0, send_idx, acc_back)
+
         grads = dict(means3D=torch.empty((P, 3), **f32), means2D=torch.empty((P, 3), **f32), opacities=torch.empty(ctx.opacities_shape, **f32))
         if sh.numel():
             grads["sh"] = torch.empty((P, M, 3), **f32)
@@ -247,11 +403,14 @@ class ShardedGaussianRasterizer(torch.nn.Module):
     full image on every rank and the local ``radii`` / ``n_touched``.  The image gradients handed to backward must be
     identical on all ranks (every rank evaluates the loss on the full image)."""
 
-    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None):
+    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "alltoall"):
         super().__init__()
+        if exchange not in ("alltoall", "allgather"):
+            raise ValueError("exchange must be 'alltoall' or 'allgather'")
         self.raster_settings = raster_settings
         self.group = group
         self.backend = backend if backend is not None else CudaBackend()
+        self.exchange = exchange
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
                 theta=None, rho=None):
@@ -260,5 +419,6 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         e = lambda t: torch.Tensor([]) if t is None else t
-        return _ShardedRasterize.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
-                                       e(theta), e(rho), self.raster_settings, self.group, self.backend)
+        fn = _ShardedRasterizeA2A if self.exchange == "alltoall" else _ShardedRasterize
+        return fn.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
+                        e(theta), e(rho), self.raster_settings, self.group, self.backend)

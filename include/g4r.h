@@ -71,6 +71,10 @@ typedef struct G4RFrame {
      * with t % tile_world == tile_rank.  Single GPU: tile_rank = 0, tile_world = 1 (a zeroed tile_world means 1). */
     int32_t tile_rank;
     int32_t tile_world;
+    /* Alternative ownership by contiguous tile-row strip [tile_row_begin, tile_row_end) (used when tile_world <= 1 and
+     * tile_row_end > tile_row_begin): the all-to-all exchange sends a splat only to the ranks whose strip it touches. */
+    int32_t tile_row_begin;
+    int32_t tile_row_end;
 } G4RFrame;
 
 /* Per-Gaussian inputs (all DEVICE pointers, contiguous, read-only). */
@@ -115,7 +119,7 @@ typedef struct G4RContext G4RContext;   /* owns one pinned int + one event; one 
 
 /* ---- library / context ------------------------------------------------------------ */
 const char* g4r_last_error(void);
-int  g4r_version(void);                               /* ABI version, currently 2 */
+int  g4r_version(void);                               /* ABI version, currently 3 */
 void g4r_struct_sizes(int32_t* out5);                 /* sizeof {G4RFrame, G4RGaussians, G4RForwardOut, G4RBackwardIO, G4RLayout}: FFI self-check */
 int  g4r_context_create(G4RContext** out);
 void g4r_context_destroy(G4RContext* ctx);
@@ -163,6 +167,9 @@ int g4r_backward(const G4RFrame* frame, const G4RGaussians* g,
  *   g4r_backward_composite : zeroes `acc` ([P_all,12] floats) and accumulates the owned tiles' screen-space gradients
  *   g4r_backward_gaussians : per-Gaussian backward of one shard from its (reduce-scattered) accumulator rows
  * g4r_backward == g4r_backward_composite + g4r_backward_gaussians on one GPU. */
+/* First / last tile row touched by each Gaussian (rows[2*i], rows[2*i+1]; 1,0 when invisible): the destinations of the
+ * all-to-all exchange.  Same rectangle arithmetic as the binning kernels. */
+int g4r_tile_rows(const G4RFrame* frame, int32_t P, const int32_t* radii, const void* geom, int32_t* rows, void* stream);
 int g4r_project_only(const G4RFrame* frame, const G4RGaussians* g, void* geom, int32_t* radii, int32_t* n_touched, void* stream);
 int g4r_count_tiles(G4RContext* ctx, const G4RFrame* frame, int32_t P_all, const int32_t* radii_all, const void* geom_all,
                     void* img, void* stream);

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_sizes():
     lib = ctypes.CDLL(LIB)
-    assert lib.g4r_version() == 2
+    assert lib.g4r_version() == 3
     for f in (lib.g4r_geom_bytes, lib.g4r_binning_bytes, lib.g4r_backward_scratch_bytes, lib.g4r_image_bytes):
         f.restype = ctypes.c_size_t
     lib.g4r_geom_bytes.argtypes = [ctypes.c_int32]
@@ -73,7 +73,7 @@ def test_python_struct_mirrors_match_the_c_layout():
     sizes = (ctypes.c_int32 * 5)()
     dgr._lib.g4r_struct_sizes(sizes)
     assert list(sizes) == [ctypes.sizeof(c) for c in (dgr._Frame, dgr._Gaussians, dgr._ForwardOut, dgr._BackwardIO, dgr._Layout)]
-    assert [n for n, _ in dgr._Frame._fields_][-2:] == ["tile_rank", "tile_world"]
+    assert [n for n, _ in dgr._Frame._fields_][-4:] == ["tile_rank", "tile_world", "tile_row_begin", "tile_row_end"]
 
 
 def test_layout_offsets_are_aligned_and_ordered():

@@ -39,7 +39,7 @@ class OracleBackend:
         d.update(kw)
         return d
 
-    def project(self, rs, M, tile_rank, tile_world, means3D, opacities, sh, colors, scales, rots, cov, geom, radii, n_touched):
+    def project(self, rs, M, means3D, opacities, sh, colors, scales, rots, cov, geom, radii, n_touched):
         nz = lambda t: t if t.numel() else None
         sc = self._scene(rs, means3D=means3D, opacities=opacities, shs=nz(sh), colors_precomp=nz(colors), scales=nz(scales),
                          rotations=nz(rots), cov3D_precomp=nz(cov))
@@ -71,9 +71,36 @@ class OracleBackend:
         G = _Geom(*[_p(g[k]) for k in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "radii", "tiles_touched")])
         return S, keep, G, g
 
-    def render(self, rs, tile_rank, tile_world, P_all, rec_all, radii_all, n_touched_all, images, img_state, cap_hint):
+    @staticmethod
+    def _owned(owner, gx, gy):
+        t = np.arange(gx * gy)
+        if owner[0] == "mod":
+            return (t % owner[2]) == owner[1]
+        return ((t // gx) >= owner[1]) & ((t // gx) < owner[2])
+
+    def tile_rows(self, rs, P, radii, geom):
+        rec = geom[: P * 48].view(torch.float32).view(P, 12).numpy()
+        W, H = int(rs.image_width), int(rs.image_height)
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        r = radii[:P].numpy()
+        rf = r.astype(np.float32)
+        px, py = rec[:, 0], rec[:, 1]
+        f2i = lambda v: np.clip(np.trunc(v), -2**31, 2**31 - 1).astype(np.int64)
+        x0 = np.minimum(gx, np.maximum(0, f2i((px - rf) * np.float32(0.0625))))
+        y0 = np.minimum(gy, np.maximum(0, f2i((py - rf) * np.float32(0.0625))))
+        x1 = np.minimum(gx, np.maximum(0, f2i((((px + rf) + np.float32(16)) + np.float32(-1)) * np.float32(0.0625))))
+        y1 = np.minimum(gy, np.maximum(0, f2i((((py + rf) + np.float32(16)) + np.float32(-1)) * np.float32(0.0625))))
+        vis = (r > 0) & (x1 > x0) & (y1 > y0)
+        rows = np.stack([np.where(vis, y0, 1), np.where(vis, y1 - 1, 0)], 1).astype(np.int32)
+        return torch.from_numpy(rows)
+
+    def render(self, rs, owner, P_all, rec_all, radii_all, n_touched_all, images, img_state, cap_hint):
         from oracle.g4r_oracle import _p
+        rec_all, radii_all, n_touched_all = rec_all[:max(P_all, 1)], radii_all[:max(P_all, 1)], n_touched_all[:max(P_all, 1)]
+        if P_all == 0:
+            radii_all = radii_all * 0
         S, keep, G, g = self._all_scene(rs, rec_all, radii_all)
+        P_all = rec_all.shape[0]
         W, H = S.W, S.H
         gx, gy = (W + 15) // 16, (H + 15) // 16
         # tiles_touched from the rectangles (oracle_bin needs it): recompute through a throw-away pass of get_rect semantics
@@ -93,7 +120,7 @@ class OracleBackend:
         N = int(self.o._bin(ctypes.byref(S), ctypes.byref(G), ctypes.byref(pl_ptr), ctypes.c_void_p(_p(ranges))))
         pl = np.ctypeslib.as_array(ctypes.cast(pl_ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(max(N, 1),))[:N].copy()
         self.o._free(pl_ptr)
-        owned = (np.arange(gx * gy) % tile_world) == tile_rank
+        owned = self._owned(owner, gx, gy)
         ranges[~owned] = 0                                     # this rank composites only its tiles
         color, depth, opac = np.zeros((3, H, W), np.float32), np.zeros((1, H, W), np.float32), np.zeros((1, H, W), np.float32)
         final_T, n_contrib, n_touched = np.zeros((H, W), np.float32), np.zeros((H, W), np.uint32), np.zeros(P_all, np.int32)
@@ -108,13 +135,15 @@ class OracleBackend:
         images[3:4].copy_(torch.from_numpy(depth * mask))
         images[4:5].copy_(torch.from_numpy(opac * mask))
         n_touched_all.copy_(torch.from_numpy(n_touched))
-        state = dict(pl=plc, ranges=ranges, final_T=final_T, n_contrib=n_contrib, N=N)
+        state = dict(pl=plc, ranges=ranges, final_T=final_T, n_contrib=n_contrib, N=N, radii=radii_all.clone())
         return state, N
 
-    def composite_backward(self, rs, tile_rank, tile_world, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):
+    def composite_backward(self, rs, owner, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):
         from oracle.g4r_oracle import _p
         st = binning
-        S, keep, G, g = self._all_scene(rs, rec_all, torch.from_numpy(self._radii_all))
+        rec_all = rec_all[:max(P_all, 1)]
+        S, keep, G, g = self._all_scene(rs, rec_all, st["radii"])
+        P_all = rec_all.shape[0]
         acc = np.zeros((P_all, 10), np.float64)
         gc = np.ascontiguousarray(grad_color.numpy().astype(np.float32))
         gd = np.ascontiguousarray(grad_depth.numpy().astype(np.float32))
@@ -123,7 +152,7 @@ class OracleBackend:
                              ctypes.c_void_p(_p(gd)), ctypes.c_void_p(_p(acc)))
         out = np.zeros((P_all, 12), np.float32)
         out[:, :10] = acc
-        acc_all.copy_(torch.from_numpy(out))
+        acc_all[:P_all].copy_(torch.from_numpy(out))
 
     def gaussian_backward(self, rs, M, means3D, sh, colors, scales, rots, cov, radii, geom, acc, grads, tau):
         from oracle.g4r_oracle import _Geom, _Grads, _p
@@ -150,7 +179,7 @@ class OracleBackend:
         tau[:6].copy_(torch.from_numpy(o["dL_dtau"]))
 
 
-def _worker(rank, world, port, P, out_dir):
+def _worker(rank, world, port, P, out_dir, exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -166,16 +195,10 @@ def _worker(rank, world, port, P, out_dir):
                                            scale_modifier=1.0, viewmatrix=sc.viewmatrix, projmatrix=sc.projmatrix,
                                            projmatrix_raw=sc.projmatrix_raw, sh_degree=sc.sh_degree, campos=sc.campos, prefiltered=False, debug=False)
     be = OracleBackend()
-    orig_render = be.render
-
-    def render(rs_, tr, tw, P_all, rec_all, radii_all, *a):
-        be._radii_all = radii_all.numpy().copy()
-        return orig_render(rs_, tr, tw, P_all, rec_all, radii_all, *a)
-    be.render = render
     leaf = {k: getattr(sc, k)[lo:hi].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
     m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
     theta, rho = torch.zeros(3, requires_grad=True), torch.zeros(3, requires_grad=True)
-    r = sharded.ShardedGaussianRasterizer(rs, backend=be)
+    r = sharded.ShardedGaussianRasterizer(rs, backend=be, exchange=exchange)
     color, radii, depth, opacity, n_touched = r(means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf["shs"],
                                                 scales=leaf["scales"], rotations=leaf["rotations"], theta=theta, rho=rho)
     ((color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()).backward()
@@ -187,7 +210,11 @@ def _worker(rank, world, port, P, out_dir):
 
 
 def test_shard_bounds_partition():
-    from diff_gaussian_rasterization.sharded import shard_bounds, owned_tiles
+    from diff_gaussian_rasterization.sharded import shard_bounds, owned_tiles, strip_bounds
+    for ty in (1, 7, 30, 60):
+        for world in (1, 2, 3, 8):
+            b = [strip_bounds(ty, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == ty and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
     for P in (0, 1, 7, 100, 1001):
         for world in (1, 2, 3, 8):
             edges = [shard_bounds(P, world, r) for r in range(world)]
@@ -198,11 +225,11 @@ def test_shard_bounds_partition():
     assert bool((masks.sum(0) == 1).all())
 
 
-@pytest.mark.parametrize("P", [1500, 1501])
-def test_sharded_render_matches_single_process_oracle(tmp_path, P):
+@pytest.mark.parametrize("P,exchange", [(1500, "allgather"), (1501, "allgather"), (1500, "alltoall"), (1501, "alltoall")])
+def test_sharded_render_matches_single_process_oracle(tmp_path, P, exchange):
     world = 2
-    port = 29000 + os.getpid() % 2000 + P % 7
-    mp.spawn(_worker, args=(world, port, P, str(tmp_path)), nprocs=world, join=True)
+    port = 29000 + os.getpid() % 2000 + P % 7 + (11 if exchange == "alltoall" else 0)
+    mp.spawn(_worker, args=(world, port, P, str(tmp_path), exchange), nprocs=world, join=True)
     sys.path.insert(0, ROOT)
     from tools import runners
     from tools.scenes import make_scene

@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--exchange", default="alltoall,allgather")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -37,11 +38,11 @@ def main():
     rs = runners.settings_for(sc, dgr)
     lo, hi = sharded.shard_bounds(sc.P, world, rank)
 
-    def run_sharded():
+    def run_sharded(exchange="alltoall"):
         leaf = {k: getattr(sc, k)[lo:hi].detach().clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
         m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
         theta, rho = torch.zeros(3, device=dev, requires_grad=True), torch.zeros(3, device=dev, requires_grad=True)
-        r = sharded.ShardedGaussianRasterizer(rs)
+        r = sharded.ShardedGaussianRasterizer(rs, exchange=exchange)
         color, radii, depth, opacity, n_touched = r(means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf["shs"],
                                                     scales=leaf["scales"], rotations=leaf["rotations"], theta=theta, rho=rho)
         ((color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()).backward()
@@ -65,21 +66,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    out = run_sharded()
     single = runners.run_public_api(sc, dgr)           # the whole cloud on this GPU
     rep = {}
-    for k in ("color", "depth", "opacity"):
-        rep[k + "_bit_identical"] = bool(torch.equal(out[k], single[k]))
-    rep["radii_equal"] = bool(torch.equal(out["radii"], single["radii"][lo:hi]))
-    rep["n_touched_equal"] = bool(torch.equal(out["n_touched"], single["n_touched"][lo:hi]))
-    for k in ("dL_dmeans3D", "dL_dscales", "dL_drots", "dL_dopacity", "dL_dshs", "dL_dmeans2D"):
-        a, b = out[k].double().reshape(-1), single[k][lo:hi].double().reshape(-1)
-        rep[k + "_l2_rel"] = float((a - b).norm() / b.norm())
-    a, b = out["dL_dtau"].double(), single["dL_dtau"].double()
-    rep["dL_dtau_l2_rel"] = float((a - b).norm() / b.norm())
-    ms_sharded = timeit(run_sharded)
+    for ex in args.exchange.split(","):
+        out = run_sharded(ex)
+        for k in ("color", "depth", "opacity"):
+            rep[f"{ex}_{k}_bit_identical"] = bool(torch.equal(out[k], single[k]))
+        rep[f"{ex}_radii_equal"] = bool(torch.equal(out["radii"], single["radii"][lo:hi]))
+        rep[f"{ex}_n_touched_equal"] = bool(torch.equal(out["n_touched"], single["n_touched"][lo:hi]))
+        for k in ("dL_dmeans3D", "dL_dscales", "dL_drots", "dL_dopacity", "dL_dshs", "dL_dmeans2D"):
+            a, b = out[k].double().reshape(-1), single[k][lo:hi].double().reshape(-1)
+            rep[f"{ex}_{k}_l2_rel"] = float((a - b).norm() / b.norm())
+        a, b = out["dL_dtau"].double(), single["dL_dtau"].double()
+        rep[f"{ex}_dL_dtau_l2_rel"] = float((a - b).norm() / b.norm())
+        rep[f"ms_fwd_bwd_sharded_{ex}"] = timeit(lambda: run_sharded(ex))
     ms_single = timeit(lambda: runners.run_public_api(sc, dgr))
-    rep.update(workload=args.workload, world=world, P=sc.P, ms_fwd_bwd_sharded=ms_sharded, ms_fwd_bwd_single_gpu=ms_single)
+    rep.update(workload=args.workload, world=world, P=sc.P, ms_fwd_bwd_single_gpu=ms_single)
     gathered = [None] * world
     dist.all_gather_object(gathered, rep)
     if rank == 0:
