@@ -3,7 +3,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <map>
+#include <mutex>
 #include <new>
+#include <string>
 
 static thread_local char g_err[512] = "";
 
@@ -56,6 +60,20 @@ struct G4RContext {
     bool pending;
     int renders_since_project;   // > 0: the scatter cursors of the current image state are dirty
 };
+
+// Experiment switches: G4R_TUNE_<NAME> in the environment, read once per name.
+int g4r_tunable(const char* name, int dflt) {
+    static std::mutex mu;
+    static std::map<std::string, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(name);
+    if (it != cache.end()) return it->second;
+    const std::string key = std::string("G4R_TUNE_") + name;
+    const char* v = getenv(key.c_str());
+    const int val = (v && *v) ? atoi(v) : dflt;
+    cache[name] = val;
+    return val;
+}
 
 static int check_frame(const G4RFrame* f, bool backward) {
     if (!f) return g4r_set_error(G4R_EINVAL, "frame is NULL");

@@ -23,14 +23,25 @@
 // 2. exclusive scan over tiles (single CTA; tiles <= a few 10^4)
 // ---------------------------------------------------------------------------------------------
 #define SCAN_THREADS 1024
+#define ORDER_BUCKETS 256
+// Also emits `order`: the tiles grouped into ORDER_BUCKETS classes of decreasing instance count (a counting sort on
+// count/max).  The per-tile kernels map blockIdx.x through it, so the hardware block scheduler starts the heaviest
+// tiles first and the light ones fill the tail (longest-processing-time-first); results do not depend on it.
 __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
-                                                                 uint32_t* __restrict__ header, int tiles) {
+                                                                 uint32_t* __restrict__ header, uint32_t* __restrict__ order, int tiles) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_wmax[SCAN_THREADS / 32];
+    __shared__ uint32_t s_bucket[ORDER_BUCKETS];
     const int per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
     const int t0 = threadIdx.x * per, t1 = min(tiles, t0 + per);
-    uint32_t sum = 0;
-    for (int t = t0; t < t1; ++t) sum += counts[(size_t)t * G4R_COUNT_STRIDE];
-    // block-wide exclusive scan of `sum`
+    if (threadIdx.x < ORDER_BUCKETS) s_bucket[threadIdx.x] = 0;
+    uint32_t sum = 0, cmax = 0;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t c = counts[(size_t)t * G4R_COUNT_STRIDE];
+        sum += c;
+        cmax = max(cmax, c);
+    }
+    // block-wide exclusive scan of `sum`, block-wide max of the counts
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = sum;
 #pragma unroll
@@ -38,8 +49,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __res
         const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += o;
     }
+    cmax = __reduce_max_sync(0xffffffffu, cmax);
     if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_wmax[warp] = cmax;
     __syncthreads();
+    cmax = __reduce_max_sync(0xffffffffu, s_wmax[lane]);
+    const float to_bucket = cmax ? (float)(ORDER_BUCKETS - 1) / (float)cmax : 0.0f;
     if (warp == 0) {
         uint32_t w = s_warp[lane];
         uint32_t wi = w;
@@ -58,6 +73,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __res
         counts[(size_t)t * G4R_COUNT_STRIDE] = 0;     // the same word becomes the scatter cursor of this tile
         ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
         run += c;
+        const int b = ORDER_BUCKETS - 1 - min(ORDER_BUCKETS - 1, (int)((float)c * to_bucket));   // heaviest -> bucket 0
+        atomicAdd(&s_bucket[b], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {                            // exclusive scan of the 256 bucket sizes (8 per lane)
+        uint32_t v[ORDER_BUCKETS / 32], tot = 0;
+#pragma unroll
+        for (int i = 0; i < ORDER_BUCKETS / 32; ++i) { v[i] = s_bucket[lane * (ORDER_BUCKETS / 32) + i]; tot += v[i]; }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        uint32_t start = inc - tot;
+#pragma unroll
+        for (int i = 0; i < ORDER_BUCKETS / 32; ++i) { s_bucket[lane * (ORDER_BUCKETS / 32) + i] = start; start += v[i]; }
+    }
+    __syncthreads();
+    for (int t = t0; t < t1; ++t) {
+        const uint2 r = ranges[t];
+        const int b = ORDER_BUCKETS - 1 - min(ORDER_BUCKETS - 1, (int)((float)(r.y - r.x) * to_bucket));
+        order[atomicAdd(&s_bucket[b], 1u)] = (uint32_t)t;
     }
 }
 
@@ -65,7 +103,8 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
     const ImageLayout il(f.width, f.height);
     char* b = (char*)img;
     g4r_stage_begin(ST_TILE_SCAN, s);
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)(b + il.counts), (uint2*)(b + il.ranges), (uint32_t*)(b + il.header), il.tiles);
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)(b + il.counts), (uint2*)(b + il.ranges), (uint32_t*)(b + il.header),
+                                                (uint32_t*)(b + il.order), il.tiles);
     g4r_stage_end(ST_TILE_SCAN, s);
     G4R_LAUNCH_OK("tile_scan_kernel");
     return G4R_OK;
@@ -245,12 +284,13 @@ static __device__ void bitonic_sort(unsigned long long* s_key, uint32_t n) {
 // bitonic network; larger tiles the CTA-local radix sort in global memory.  All three produce the same total order.
 __global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __restrict__ ranges, uint2* __restrict__ pairs,
                                                               uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list,
-                                                              const uint32_t* __restrict__ header, uint32_t capacity) {
+                                                              const uint32_t* __restrict__ header, uint32_t capacity,
+                                                              const uint32_t* __restrict__ order) {
     if (header[0] > capacity) return;
     __shared__ __align__(16) unsigned long long s_key[SORT_SMEM_MAX];     // bucket path: [0,2048) input, [2048,4096) output
     __shared__ uint32_t s_cnt[BUCKET_MAX_L];                               // bucket counters / cursors
     __shared__ uint32_t s_red[2 * (G4R_BLOCK / 32)];
-    const uint2 range = ranges[blockIdx.x];
+    const uint2 range = ranges[order ? order[blockIdx.x] : blockIdx.x];
     const uint32_t L = range.y - range.x;
     if (L == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -373,9 +413,11 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
                                                                          (uint32_t)il.tiles_y, g4r_owner(f));
     g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");
+    static const bool lpt = g4r_tunable("LPT", 1) != 0;
     g4r_stage_begin(ST_TILE_SORT, s);
     tile_sort_kernel<<<il.tiles, G4R_BLOCK, 0, s>>>((const uint2*)(ib + il.ranges), (uint2*)(bb + bl.pairs), (uint2*)(bb + bl.pairs_alt),
-                                                    (uint32_t*)(bb + bl.point_list), (const uint32_t*)(ib + il.header), cap);
+                                                    (uint32_t*)(bb + bl.point_list), (const uint32_t*)(ib + il.header), cap,
+                                                    lpt ? (const uint32_t*)(ib + il.order) : nullptr);
     g4r_stage_end(ST_TILE_SORT, s);
     G4R_LAUNCH_OK("tile_sort_kernel");
     return G4R_OK;

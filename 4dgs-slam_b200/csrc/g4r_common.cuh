@@ -44,7 +44,7 @@ struct GeomLayout {      // per-Gaussian state, saved for backward
     }
 };
 struct ImageLayout {     // per-pixel + per-tile state, saved for backward
-    size_t header, counts, ranges, final_T, n_contrib, total;
+    size_t header, counts, ranges, final_T, n_contrib, order, total;
     int tiles_x, tiles_y, tiles;
     __host__ __device__ ImageLayout(int W, int H) {
         tiles_x = (W + G4R_TILE - 1) / G4R_TILE;
@@ -56,6 +56,7 @@ struct ImageLayout {     // per-pixel + per-tile state, saved for backward
         ranges = o;    o = g4r_align(o + (size_t)tiles * 8);
         final_T = o;   o = g4r_align(o + (size_t)W * H * 4);
         n_contrib = o; o = g4r_align(o + (size_t)W * H * 4);
+        order = o;     o = g4r_align(o + (size_t)tiles * 4);                       // tiles, heaviest first (launch order)
         total = o + 256;
     }
 };
@@ -116,6 +117,9 @@ int g4r_set_error(int code, const char* fmt, ...);
 enum G4RStage { ST_PROJECT = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_COMPOSITE_FWD, ST_COMPOSITE_BWD, ST_GAUSSIAN_BWD, ST_COUNT };
 void g4r_stage_begin(int stage, cudaStream_t s);
 void g4r_stage_end(int stage, cudaStream_t s);
+
+// Experiment switches (environment, read once per process): G4R_TUNE_<NAME>=<int>.  Defaults are the measured best.
+int g4r_tunable(const char* name, int dflt);
 
 // Tile ownership of the sharded render: interleaved (t % world == rank) or a contiguous strip of tile rows.
 struct TileOwner {

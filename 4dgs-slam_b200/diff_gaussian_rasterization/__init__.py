@@ -192,9 +192,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _dev_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
-    if t.dtype != torch.float32 or t.device != device:
-        t = t.to(device=device, dtype=torch.float32)
-    return t.contiguous()
+    if t.dtype is torch.float32 and t.device == device:
+        return t if t.is_contiguous() else t.contiguous()
+    return t.to(device=device, dtype=torch.float32).contiguous()
 
 
 def _make_frame(rs: "GaussianRasterizationSettings", device: torch.device, sh_coeffs: int, keep: list) -> _Frame:
@@ -289,7 +289,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             _check(_lib.g4r_forward_render(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                            binning.data_ptr(), cap, ctypes.byref(out), stream))
             _captured.append((img, cap, _layout(P, W, H, cap).img_header))
-            state = dict(P=P, N=-1, geom=geom, img=img, binning=binning, capacity=cap)
+            state = dict(P=P, N=-1, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
             return color, radii, depth, opacity, n_touched, state
 
         _check(_lib.g4r_forward_project(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
@@ -312,12 +312,12 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                            binning.data_ptr(), cap, ctypes.byref(out), stream))
         _cap_hint[key] = max(N, int(hint * 0.95))
-    state = dict(P=P, N=N, geom=geom, img=img, binning=binning, capacity=cap)
+    state = dict(P=P, N=N, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
     return color, radii, depth, opacity, n_touched, state
 
 
 def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii, geom, img, binning,
-                   opacities_shape, grad_out_color, grad_out_depth):
+                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None):
     device = means3D.device
     H, W = int(rs.image_height), int(rs.image_width)
     f32 = dict(dtype=torch.float32, device=device)
@@ -338,10 +338,12 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
     grad_out_color = _dev_f32(grad_out_color, device)
     grad_out_depth = _dev_f32(grad_out_depth, device)
     scratch = torch.empty((_lib.g4r_backward_scratch_bytes(P),), dtype=torch.uint8, device=device)
-    keep: list = []
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
-        frame = _make_frame(rs, device, M, keep)
+        # the forward's frame struct (camera pointers; the tensors behind them are kept alive next to it) is reused
+        frame, keep = frame_keep if frame_keep is not None else (None, [])
+        if frame is None:
+            frame = _make_frame(rs, device, M, keep)
         g = _make_gaussians(P, means3D, None, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
         g.opacities = means3D.data_ptr()   # opacities are not read in backward (they live in the splat records)
         io = _BackwardIO(grad_out_color.data_ptr(), grad_out_depth.data_ptr(), grad_means3D.data_ptr(), grad_means2D.data_ptr(),
@@ -371,6 +373,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.num_rendered = state["N"]
         ctx.P = state["P"]
         ctx.opacities_shape = tuple(opacities.shape)
+        ctx.frame_keep = state.get("frame")
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
                               state["geom"], state["binning"], state["img"])
         ctx.mark_non_differentiable(radii, n_touched)
@@ -390,7 +393,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _dev_f32(scales, device) if scales.numel() else scales,
             _dev_f32(rotations, device) if rotations.numel() else rotations,
             _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp,
-            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth)
+            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep)
         grad_rho = tau[:3].view(1, -1)
         grad_theta = tau[3:6].view(1, -1)
         needs = ctx.needs_input_grad

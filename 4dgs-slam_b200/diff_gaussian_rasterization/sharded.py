@@ -17,11 +17,16 @@ Global Gaussian ids are ``rank * Pmax + local index`` (shards padded to the larg
 the concatenated cloud, so every tile's sorted list -- and therefore every pixel -- is identical to the single-GPU
 result.
 
-``exchange="alltoall"`` (default) replaces steps 2 and 6 by variable-size all-to-alls: rank r owns a contiguous strip of tile
+``exchange="alltoall"`` replaces steps 2 and 6 by variable-size all-to-alls: rank r owns a contiguous strip of tile
 rows, every splat record travels only to the ranks whose strip its tile rectangle touches (~1.3 ranks instead of all),
 and the accumulator rows travel back the same way and are scatter-added at the owner.  Records arrive ordered by
-(source rank, local index) = global id order, so ties in depth still resolve like on one GPU.  ``exchange="allgather"``
-is the simpler variant described above (interleaved tile ownership).  The kernel calls go through a *backend* object so that the host logic (sharding, collectives, padding) can be
+(source rank, local index) = global id order, so ties in depth still resolve like on one GPU.  It moves ~6x fewer
+bytes at 8 ranks, but on one NVSwitch node the extra host steps (split sizes, index build, index_add) cost more than
+the bytes save (profiles/scaling/sharded_check_C4_x*.json: 1.99 ms vs 1.76 ms at 8 GPUs), so ``"allgather"`` -- the
+variant described above, interleaved tile ownership -- is the default; ``"alltoall"`` is the one to pick when the
+exchange crosses nodes.
+
+The kernel calls go through a *backend* object so that the host logic (sharding, collectives, padding) can be
 exercised with the gloo backend on CPU by the tests, which inject a CPU backend; the product default is the CUDA library
 and there is no fallback.
 """
@@ -403,7 +408,7 @@ class ShardedGaussianRasterizer(torch.nn.Module):
     full image on every rank and the local ``radii`` / ``n_touched``.  The image gradients handed to backward must be
     identical on all ranks (every rank evaluates the loss on the full image)."""
 
-    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "alltoall"):
+    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "allgather"):
         super().__init__()
         if exchange not in ("alltoall", "allgather"):
             raise ValueError("exchange must be 'alltoall' or 'allgather'")

@@ -22,11 +22,16 @@ for stage in "$@"; do
     ncuall)   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'project_kernel|tile_scan|scatter_kernel|tile_sort|composite|gaussian_backward' -s 21 -c 7 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncuall.log 2>&1; echo "rc=$?" ;;
     sharded2) for wl in C2 C4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py --workload $wl > gpurun_out/sharded_$wl.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_$wl.log; done ;;
     bench2)   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 100 --no-cpu-baseline > gpurun_out/bench_x2.json 2> gpurun_out/bench_x2.err; echo "rc=$?"; cat gpurun_out/bench_x2.json ;;
+    shard8)   for n in 2 4 8; do
+                timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n tools/sharded_check.py --workload C4 > gpurun_out/sharded_C4_x$n.log 2>&1; echo "sharded C4 x$n rc=$?"; tail -2 gpurun_out/sharded_C4_x$n.log | cut -c1-1500
+              done ;;
     scale8)   for n in 2 4 8; do
                 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 100 --no-cpu-baseline > gpurun_out/bench_x$n.json 2> gpurun_out/bench_x$n.err; echo "bench x$n rc=$?"; cut -c1-200 gpurun_out/bench_x$n.json
                 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n tools/sharded_check.py --workload C4 > gpurun_out/sharded_C4_x$n.log 2>&1; echo "sharded C4 x$n rc=$?"; tail -2 gpurun_out/sharded_C4_x$n.log | cut -c1-400
               done ;;
     matrix)   timeout 900 python tools/perf_matrix.py > gpurun_out/perf_matrix.log 2>&1; echo "rc=$?"; cat gpurun_out/perf_matrix.log | cut -c1-400 ;;
+    tune)     timeout 1200 python tools/tune_matrix.py > gpurun_out/tune_matrix.log 2>&1; echo "rc=$?"; cut -c1-300 gpurun_out/tune_matrix.log ;;
+    hostline) timeout 600 python tools/host_timeline.py > gpurun_out/host_timeline.log 2>&1; echo "rc=$?"; cut -c1-1200 gpurun_out/host_timeline.log ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
