@@ -186,10 +186,9 @@ def _worker(rank, world, port, P, out_dir, exchange):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization import sharded
-    from tools.scenes import make_scene
     # the CPU test backend bypasses the CUDA-only checks of the product module
     sharded._dev_f32 = lambda t, dev: t.float().contiguous()
-    sc = make_scene(P, 96, 64, sh_degree=1, seed=11)
+    sc = torch.load(os.path.join(out_dir, "scene.pt"), weights_only=False)     # the parent's scene, bit for bit
     lo, hi = sharded.shard_bounds(P, world, rank)
     rs = dgr.GaussianRasterizationSettings(image_height=sc.H, image_width=sc.W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=sc.bg,
                                            scale_modifier=1.0, viewmatrix=sc.viewmatrix, projmatrix=sc.projmatrix,
@@ -229,11 +228,12 @@ def test_shard_bounds_partition():
 def test_sharded_render_matches_single_process_oracle(tmp_path, P, exchange):
     world = 2
     port = 29000 + os.getpid() % 2000 + P % 7 + (11 if exchange == "alltoall" else 0)
-    mp.spawn(_worker, args=(world, port, P, str(tmp_path), exchange), nprocs=world, join=True)
     sys.path.insert(0, ROOT)
     from tools import runners
     from tools.scenes import make_scene
     sc = make_scene(P, 96, 64, sh_degree=1, seed=11)
+    torch.save(sc, os.path.join(str(tmp_path), "scene.pt"))
+    mp.spawn(_worker, args=(world, port, P, str(tmp_path), exchange), nprocs=world, join=True)
     ref = runners.run_oracle(sc)
     parts = [np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(world)]
     for z in parts:                                            # every rank holds the full, identical image

@@ -32,6 +32,8 @@ for stage in "$@"; do
     matrix)   timeout 900 python tools/perf_matrix.py > gpurun_out/perf_matrix.log 2>&1; echo "rc=$?"; cat gpurun_out/perf_matrix.log | cut -c1-400 ;;
     tune)     timeout 1200 python tools/tune_matrix.py > gpurun_out/tune_matrix.log 2>&1; echo "rc=$?"; cut -c1-300 gpurun_out/tune_matrix.log ;;
     hostline) timeout 600 python tools/host_timeline.py > gpurun_out/host_timeline.log 2>&1; echo "rc=$?"; cut -c1-1200 gpurun_out/host_timeline.log ;;
+    determinism) timeout 900 python tools/determinism_check.py > gpurun_out/determinism.log 2>&1; echo "rc=$?"; cut -c1-2500 gpurun_out/determinism.log ;;
+    repro)    timeout 900 python tools/repro_anomaly.py 16 > gpurun_out/repro_anomaly.log 2>&1; echo "rc=$?"; cut -c1-1500 gpurun_out/repro_anomaly.log ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

@@ -53,6 +53,16 @@ class Scene:
         return Scene(**kw)
 
 
+def broadcast_scene(sc: Scene, src: int = 0, group=None) -> Scene:
+    """Multi-rank runs: every rank takes rank `src`'s tensors, so that all ranks hold the bit-identical scene (the CPU
+    generator's float64 transcendental / reduction kernels are not guaranteed to round identically in every process)."""
+    import torch.distributed as dist
+    for k, v in sc.__dict__.items():
+        if isinstance(v, torch.Tensor):
+            dist.broadcast(v, src=src, group=group)
+    return sc
+
+
 def _se3_exp(rho: torch.Tensor, theta: torch.Tensor) -> torch.Tensor:
     """SE(3) exponential (float64) used only to produce a generic, non-axis-aligned test pose."""
     W = torch.tensor([[0, -theta[2], theta[1]], [theta[2], 0, -theta[0]], [-theta[1], theta[0], 0]], dtype=torch.float64)
@@ -132,7 +142,10 @@ def make_scene(P: int, W: int, H: int, sh_degree: int = 0, sh_coeffs: Optional[i
     else:
         T_w2c = torch.eye(4, dtype=torch.float64)
     R, t = T_w2c[:3, :3], T_w2c[:3, 3]
-    pw = (pc - t) @ R                                      # world points: R^T (pc - t)
+    # world points R^T (pc - t), written element-wise: BLAS results depend on buffer alignment, which would make the cloud
+    # differ in the last bit between processes (seen as 1-ulp image differences between ranks / runs)
+    d = pc - t
+    pw = torch.stack([d[:, 0] * R[0, j] + d[:, 1] * R[1, j] + d[:, 2] * R[2, j] for j in range(3)], dim=1)
     cam = camera_matrices(W, H, fx, fy, cx, cy, R, t)
 
     r_px = torch.exp(U(P * 3, math.log(px_min), math.log(px_max))).view(P, 3)

@@ -31,10 +31,10 @@ def main():
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization import sharded
     from tools import runners
-    from tools.scenes import config_scene, make_scene
+    from tools.scenes import broadcast_scene, config_scene, make_scene
 
     sc_cpu = config_scene(args.workload) if args.workload.startswith("C") else make_scene(20000, 320, 240, sh_degree=2, seed=5)
-    sc = sc_cpu.to(dev)
+    sc = broadcast_scene(sc_cpu.to(dev))       # all ranks render rank 0's (bit-identical) scene
     rs = runners.settings_for(sc, dgr)
     lo, hi = sharded.shard_bounds(sc.P, world, rank)
 

@@ -15,19 +15,23 @@ sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
 
 VARIANTS = {
     "default": {},
-    "previous (no LPT, driver carveout)": {"LPT": 0, "BWD_CARVEOUT": -1},
-    "no LPT": {"LPT": 0},
+    "no LPT (tiles in index order)": {"LPT": 0},
     "bwd driver carveout": {"BWD_CARVEOUT": -1},
-    "fwd 9 CTA/SM (56 regs)": {"FWD_MINB": 9},
-    "fwd 10 CTA/SM (48 regs)": {"FWD_MINB": 10},
-    "fwd 9 CTA/SM + carveout 100": {"FWD_MINB": 9, "FWD_CARVEOUT": 100},
-    "bwd tile CTA, batch 64": {"BWD_VARIANT": 1},
-    "bwd half-tile CTA, batch 128": {"BWD_VARIANT": 2},
-    "bwd half-tile CTA, batch 64": {"BWD_VARIANT": 3},
 }
+# Round-1 history (profiles/r01_v7_tune_matrix.json) also covered shapes that were measured and dropped from the source:
+# forward capped at 56 / 48 registers (9 / 10 CTAs per SM), backward CTA per tile with 64 / 128 staged splats, backward CTA
+# per half tile with 128 staged.
+
+
+SCENE_FILE = "/tmp/g4r_tune_scenes.pt"
 
 
 def scenes():
+    """Built once by the parent and shared through a file: the CPU generator is not guaranteed to round identically in
+    every process, and the variants are compared by output hash."""
+    import torch
+    if os.path.exists(SCENE_FILE):
+        return torch.load(SCENE_FILE, weights_only=False)
     from tools.perf_matrix import clustered
     from tools.scenes import config_scene, make_scene
     return {
@@ -75,6 +79,10 @@ def worker():
 
 
 def main():
+    import torch
+    if os.path.exists(SCENE_FILE):
+        os.remove(SCENE_FILE)
+    torch.save(scenes(), SCENE_FILE)
     results = {}
     for vname, env_add in VARIANTS.items():
         env = dict(os.environ)
