@@ -19,7 +19,9 @@ for stage in "$@"; do
     benchref) timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches.log 2>&1; echo "rc=$?" ;;
     ncufull)  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:composite -s 4 -c 4 -o gpurun_out/prof_composite -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncufull.log 2>&1; echo "rc=$?" ;;
-    ncuall)   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'project_kernel|tile_scan|scatter_kernel|tile_sort|composite|gaussian_backward' -s 21 -c 7 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncuall.log 2>&1; echo "rc=$?" ;;
+    ncuall)   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'project_kernel|tile_scan|scatter_kernel|tile_sort|composite|gaussian_backward' -s 21 -c 7 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncuall.log 2>&1; echo "rc=$?"
+              # summarise on the box so that a bench stage later in this session reports this capture's DRAM traffic
+              python tools/ncu_summary.py gpurun_out/prof_all.ncu-rep "${G4R_TAG:-r01_v7}" && cp profiles/ncu_traffic.json profiles/${G4R_TAG:-r01_v7}_ncu_summary.md gpurun_out/ ;;
     sharded2) for wl in C2 C4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py --workload $wl > gpurun_out/sharded_$wl.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_$wl.log; done ;;
     bench2)   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 100 --no-cpu-baseline > gpurun_out/bench_x2.json 2> gpurun_out/bench_x2.err; echo "rc=$?"; cat gpurun_out/bench_x2.json ;;
     shard8)   for n in 2 4 8; do
