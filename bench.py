@@ -303,14 +303,15 @@ def timed_steps(step, steps, warmup, flush, dist_barrier, sampler=None):
     return [a.elapsed_time(b) for a, b in ev], clocks
 
 
-def cpu_baseline(wl: Workload, max_frames=3, budget_s=25.0):
-    """The CPU oracle (a port of the reference algorithm) on the host cores: fwd+bwd frames/s over a bounded sample."""
+def cpu_baseline(wl: Workload, min_s=10.0, max_frames=200, budget_s=25.0):
+    """The CPU oracle (a port of the reference algorithm) on the host cores: fwd+bwd frames/s over a bounded sample
+    (whole frames until at least `min_s` seconds of CPU work have been timed, never more than `budget_s`)."""
     from oracle.g4r_oracle import Oracle, scene_dict
     ora = Oracle("f32")
     d = scene_dict(wl.cpu)
     t0 = time.time()
     n = 0
-    while n < max_frames and (time.time() - t0) < budget_s:
+    while n < max_frames and (time.time() - t0) < (min_s if n else budget_s):
         f = ora.forward(d)
         ora.backward(f, wl.cpu.grad_color, wl.cpu.grad_depth)
         n += 1
