@@ -15,8 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
 
 VARIANTS = {
     "default": {},
-    "CTA-staged composite kernels": {"WARP_WALK": 0},
-    "no LPT (tiles in index order)": {"LPT": 0},
+    "backward staged by TMA bulk copies": {"BWD_TMA": 1},
 }
 # Round-1 history (profiles/r01_v7_tune_matrix.json) also covered shapes that were measured and dropped from the source:
 # forward capped at 56 / 48 registers (9 / 10 CTAs per SM), backward CTA per tile with 64 / 128 staged splats, backward CTA
@@ -88,8 +87,13 @@ def main():
         env = dict(os.environ)
         for k, v in env_add.items():
             env["G4R_TUNE_" + k] = str(v)
-        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker"], env=env, stdout=subprocess.PIPE,
-                           stderr=subprocess.STDOUT, text=True, timeout=600)
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker"], env=env, stdout=subprocess.PIPE,
+                               stderr=subprocess.STDOUT, text=True, timeout=240)
+        except subprocess.TimeoutExpired as exc:      # a hung kernel: the child is killed, the other variants still run
+            results[vname] = {"error": "timeout: " + str(exc.stdout)[-800:]}
+            print(vname, "TIMEOUT", flush=True)
+            continue
         line = [ln for ln in p.stdout.splitlines() if ln.startswith("TUNE_RESULT ")]
         if p.returncode != 0 or not line:
             results[vname] = {"error": p.stdout[-1500:]}
