@@ -100,13 +100,19 @@ static int check_gaussians(const G4RFrame* f, const G4RGaussians* g) {
         const int K = (f->sh_degree + 1) * (f->sh_degree + 1);
         if (f->sh_coeffs < K) return g4r_set_error(G4R_EINVAL, "sh_degree %d needs %d coefficients but sh has %d", f->sh_degree, K, f->sh_coeffs);
     }
+    if (g->activation != G4R_ACT_NONE && g->activation != G4R_ACT_RAW) return g4r_set_error(G4R_EINVAL, "unknown activation mode %d", g->activation);
+    if (g->activation == G4R_ACT_RAW) {
+        if (!g->shs || !has_sr) return g4r_set_error(G4R_EINVAL, "raw-parameter mode needs features_dc, scaling and rotation");
+        if (f->sh_coeffs > 1 && !g->shs_rest) return g4r_set_error(G4R_EINVAL, "raw-parameter mode with %d SH coefficients needs features_rest", f->sh_coeffs);
+        if (g->scale_dim != 0 && g->scale_dim != 1 && g->scale_dim != 3) return g4r_set_error(G4R_EINVAL, "scale_dim must be 1 or 3");
+    }
     return G4R_OK;
 }
 
 extern "C" {
 
 const char* g4r_last_error(void) { return g_err; }
-int g4r_version(void) { return 3; }
+int g4r_version(void) { return 4; }
 void g4r_struct_sizes(int32_t* out5) {
     out5[0] = (int32_t)sizeof(G4RFrame); out5[1] = (int32_t)sizeof(G4RGaussians); out5[2] = (int32_t)sizeof(G4RForwardOut);
     out5[3] = (int32_t)sizeof(G4RBackwardIO); out5[4] = (int32_t)sizeof(G4RLayout);
@@ -240,6 +246,8 @@ int g4r_backward_gaussians(const G4RFrame* f, const G4RGaussians* g, const int32
     if (g->P == 0) return G4R_OK;
     if (!io->dL_dmeans3D || !io->dL_dmeans2D || !io->dL_dopacity) return g4r_set_error(G4R_EINVAL, "dL_dmeans3D/dL_dmeans2D/dL_dopacity are NULL");
     if (g->shs && !io->dL_dshs) return g4r_set_error(G4R_EINVAL, "dL_dshs is NULL although shs was given");
+    if (g->activation == G4R_ACT_RAW && f->sh_coeffs > 1 && !io->dL_dshs_rest) return g4r_set_error(G4R_EINVAL, "dL_dshs_rest is NULL in raw-parameter mode");
+    if (g->activation == G4R_ACT_RAW && (!io->dL_dscales || !io->dL_drotations)) return g4r_set_error(G4R_EINVAL, "raw-parameter mode writes dL_dscales and dL_drotations");
     if (!radii || !geom || !acc) return g4r_set_error(G4R_EINVAL, "saved state / accumulators are NULL");
     if (((uintptr_t)geom | (uintptr_t)acc) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
     if (io->dL_drotations && ((uintptr_t)io->dL_drotations & 15u)) return g4r_set_error(G4R_EINVAL, "dL_drotations must be 16-byte aligned");

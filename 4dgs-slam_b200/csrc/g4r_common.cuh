@@ -118,6 +118,17 @@ enum G4RStage { ST_PROJECT = 0, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_COMPO
 void g4r_stage_begin(int stage, cudaStream_t s);
 void g4r_stage_end(int stage, cudaStream_t s);
 
+// ---- raw-parameter mode: the activations of GaussianModel (gaussian_model.py:100-128), one fixed operation order that
+// the CPU restatement under oracle/ follows: sigmoid = 1/(1+exp(-x)) (torch's CUDA sigmoid), exp = expf, normalize = q / max(|q|, 1e-12)
+// (torch.nn.functional.normalize), |q|^2 accumulated r,x,y,z with fused multiply-adds.
+#ifdef __CUDACC__
+static __device__ __forceinline__ float g4r_sigmoid(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+static __device__ __forceinline__ float g4r_quat_norm(float qr, float qx, float qy, float qz) {
+    const float n2 = __fmaf_rn(qz, qz, __fmaf_rn(qy, qy, __fmaf_rn(qx, qx, __fmul_rn(qr, qr))));
+    return fmaxf(__fsqrt_rn(n2), 1e-12f);
+}
+#endif
+
 // Experiment switches (environment, read once per process): G4R_TUNE_<NAME>=<int>.  Defaults are the measured best.
 int g4r_tunable(const char* name, int dflt);
 

@@ -19,13 +19,14 @@
 struct GaussBwdParams {
     int P, D, M, W, H;
     float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
-    const float *means3D, *shs, *colors_precomp, *scales, *rotations, *cov3D_precomp;
+    const float *means3D, *shs, *shs_rest, *colors_precomp, *scales, *rotations, *cov3D_precomp;
+    int scale_dim;                // raw mode: 1 = isotropic _scaling [P,1]
     const float *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
     const int32_t* radii;
     const float4* rec;
     const uint8_t* clamped;
     const float* acc;
-    float *dL_dmeans3D, *dL_dmeans2D, *dL_dopacity, *dL_dshs, *dL_dcolors_precomp, *dL_dscales, *dL_drotations, *dL_dcov3D;
+    float *dL_dmeans3D, *dL_dmeans2D, *dL_dopacity, *dL_dshs, *dL_dshs_rest, *dL_dcolors_precomp, *dL_dscales, *dL_drotations, *dL_dcov3D;
     float* dL_dtau;
 };
 
@@ -33,6 +34,11 @@ struct V3 { float x, y, z; };
 static __device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 static __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
+// kRaw (G4R_ACT_RAW): inputs are GaussianModel's raw parameters; the activations are re-applied after the loads and the
+// gradients leave through the chain rule of exp / sigmoid / normalize (what autograd does for the reference's prelude,
+// gaussian_model.py:100-128): d/d_scaling = dL/ds * s, d/d_opacity = dL/do * o (1 - o), d/d_rotation = (g - q (q.g)) / |raw|;
+// SH gradients are split into the [P,1,3] and [P,M-1,3] parameter tensors.
+template <bool kRaw>
 __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const GaussBwdParams p) {
     __shared__ float s_tau[G4R_BLOCK / 32][6];
     __shared__ float v[16], pm[16];      // view / full projection matrices: broadcast reads instead of 32 live registers
@@ -52,9 +58,15 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
         p.dL_dmeans3D[o3] = 0.f; p.dL_dmeans3D[o3 + 1] = 0.f; p.dL_dmeans3D[o3 + 2] = 0.f;
         p.dL_dmeans2D[o3] = 0.f; p.dL_dmeans2D[o3 + 1] = 0.f; p.dL_dmeans2D[o3 + 2] = 0.f;
         p.dL_dopacity[i] = 0.f;
-        if (p.dL_dshs) { float* d = p.dL_dshs + (size_t)i * p.M * 3; for (int k = 0; k < p.M * 3; ++k) d[k] = 0.f; }
+        if (kRaw) {
+            float* d = p.dL_dshs + o3; d[0] = 0.f; d[1] = 0.f; d[2] = 0.f;
+            if (p.dL_dshs_rest) { float* r = p.dL_dshs_rest + (size_t)i * (p.M - 1) * 3; for (int k = 0; k < (p.M - 1) * 3; ++k) r[k] = 0.f; }
+        } else if (p.dL_dshs) { float* d = p.dL_dshs + (size_t)i * p.M * 3; for (int k = 0; k < p.M * 3; ++k) d[k] = 0.f; }
         if (p.dL_dcolors_precomp) { p.dL_dcolors_precomp[o3] = 0.f; p.dL_dcolors_precomp[o3 + 1] = 0.f; p.dL_dcolors_precomp[o3 + 2] = 0.f; }
-        if (p.dL_dscales) { p.dL_dscales[o3] = 0.f; p.dL_dscales[o3 + 1] = 0.f; p.dL_dscales[o3 + 2] = 0.f; }
+        if (p.dL_dscales) {
+            if (kRaw && p.scale_dim == 1) p.dL_dscales[i] = 0.f;
+            else { p.dL_dscales[o3] = 0.f; p.dL_dscales[o3 + 1] = 0.f; p.dL_dscales[o3 + 2] = 0.f; }
+        }
         if (p.dL_drotations) reinterpret_cast<float4*>(p.dL_drotations)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.dL_dcov3D) { float* d = p.dL_dcov3D + (size_t)i * 6; for (int k = 0; k < 6; ++k) d[k] = 0.f; }
     }
@@ -75,13 +87,23 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
         const bool has_scale = p.cov3D_precomp == nullptr;
         float c0, c1, c2, c3, c4, c5;
         float sx = 0.f, sy = 0.f, sz = 0.f, qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        float act_s[3] = {0.f, 0.f, 0.f}, qnorm = 1.f;   // raw mode: activated scales (before the modifier), |_rotation|
         float R[3][3];   // R[a][k] = reference's glm R[col a][row k]; M[a][k] = s_k * R[a][k]
         if (has_scale) {
-            sx = p.scale_modifier * __ldg(p.scales + (size_t)i * 3);
-            sy = p.scale_modifier * __ldg(p.scales + (size_t)i * 3 + 1);
-            sz = p.scale_modifier * __ldg(p.scales + (size_t)i * 3 + 2);
+            const bool iso = kRaw && p.scale_dim == 1;
+            float s0 = iso ? __ldg(p.scales + i) : __ldg(p.scales + (size_t)i * 3);
+            float s1 = iso ? s0 : __ldg(p.scales + (size_t)i * 3 + 1);
+            float s2 = iso ? s0 : __ldg(p.scales + (size_t)i * 3 + 2);
+            if (kRaw) { s0 = expf(s0); s1 = iso ? s0 : expf(s1); s2 = iso ? s0 : expf(s2); act_s[0] = s0; act_s[1] = s1; act_s[2] = s2; }
+            sx = p.scale_modifier * s0;
+            sy = p.scale_modifier * s1;
+            sz = p.scale_modifier * s2;
             qr = __ldg(p.rotations + (size_t)i * 4); qx = __ldg(p.rotations + (size_t)i * 4 + 1);
             qy = __ldg(p.rotations + (size_t)i * 4 + 2); qz = __ldg(p.rotations + (size_t)i * 4 + 3);
+            if (kRaw) {
+                qnorm = g4r_quat_norm(qr, qx, qy, qz);
+                qr = __fdiv_rn(qr, qnorm); qx = __fdiv_rn(qx, qnorm); qy = __fdiv_rn(qy, qnorm); qz = __fdiv_rn(qz, qnorm);
+            }
             R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
             R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
             R[2][0] = 2.f * (qx * qz - qr * qy); R[2][1] = 2.f * (qy * qz + qr * qx); R[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
@@ -204,10 +226,14 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
             const V3 dir_orig = v3(mx - __ldg(p.campos), my - __ldg(p.campos + 1), mz - __ldg(p.campos + 2));
             const float len = sqrtf(dot(dir_orig, dir_orig));
             const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-            const float* sh = p.shs + (size_t)i * p.M * 3;
-            float* dsh = p.dL_dshs + (size_t)i * p.M * 3;
-#define SHV(k) v3(__ldg(sh + (k) * 3), __ldg(sh + (k) * 3 + 1), __ldg(sh + (k) * 3 + 2))
-#define DSH(k, f) { const float f__ = (f); dsh[(k) * 3] = f__ * dRGB.x; dsh[(k) * 3 + 1] = f__ * dRGB.y; dsh[(k) * 3 + 2] = f__ * dRGB.z; }
+            // raw mode: coefficient 0 <-> _features_dc [P,1,3], coefficients 1.. <-> _features_rest [P,M-1,3]
+            const bool split = kRaw && p.M > 1;
+            const float* sh = kRaw ? p.shs + (size_t)i * 3 : p.shs + (size_t)i * p.M * 3;
+            const float* shr = split ? p.shs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : sh;
+            float* dsh = kRaw ? p.dL_dshs + (size_t)i * 3 : p.dL_dshs + (size_t)i * p.M * 3;
+            float* dshr = split ? p.dL_dshs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : dsh;
+#define SHV(k) v3(__ldg(((k) == 0 ? sh : shr) + (k) * 3), __ldg(((k) == 0 ? sh : shr) + (k) * 3 + 1), __ldg(((k) == 0 ? sh : shr) + (k) * 3 + 2))
+#define DSH(k, f) { const float f__ = (f); float* d__ = ((k) == 0 ? dsh : dshr) + (k) * 3; d__[0] = f__ * dRGB.x; d__[1] = f__ * dRGB.y; d__[2] = f__ * dRGB.z; }
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;    // dL/d(dir) accumulated as dot(dRGB/d(dir), dRGB)
             DSH(0, G4R_SH_C0);
             if (p.D > 0) {
@@ -241,7 +267,7 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
                     }
                 }
             }
-            for (int k = K * 3; k < p.M * 3; ++k) dsh[k] = 0.f;     // inactive coefficients (reference: torch::zeros)
+            for (int k = K * 3; k < p.M * 3; ++k) dshr[k] = 0.f;    // inactive coefficients (reference: torch::zeros); K >= 1
 #undef SHV
 #undef DSH
             // d normalize(v)/dv applied to dL/d(dir) (auxiliary.h:109-120)
@@ -270,9 +296,16 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
 #pragma unroll
                 for (int k = 0; k < 3; ++k) N[a][k] = 2.f * sk[k] * (dS[a][0] * R[0][k] + dS[a][1] * R[1][k] + dS[a][2] * R[2][k]);
             if (p.dL_dscales) {
-                float* d = p.dL_dscales + (size_t)i * 3;
+                float ds[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) d[k] = R[0][k] * N[0][k] + R[1][k] * N[1][k] + R[2][k] * N[2][k];
+                for (int k = 0; k < 3; ++k) ds[k] = R[0][k] * N[0][k] + R[1][k] * N[1][k] + R[2][k] * N[2][k];
+                if (kRaw) {                                                   // d exp(x) = exp(x) dx
+                    if (p.scale_dim == 1) p.dL_dscales[i] = (ds[0] + ds[1] + ds[2]) * act_s[0];
+                    else { float* d = p.dL_dscales + (size_t)i * 3; d[0] = ds[0] * act_s[0]; d[1] = ds[1] * act_s[1]; d[2] = ds[2] * act_s[2]; }
+                } else {
+                    float* d = p.dL_dscales + (size_t)i * 3;
+                    d[0] = ds[0]; d[1] = ds[1]; d[2] = ds[2];
+                }
             }
             // G[k][a] = dL/dR entries scaled by s_k: reference dL_dMt[k] *= s_k  -> G[k][a] = s_k * N[a][k]
             float Gm[3][3];
@@ -286,6 +319,11 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
                 dq.y = 2.f * qy * (Gm[1][0] + Gm[0][1]) + 2.f * qz * (Gm[2][0] + Gm[0][2]) + 2.f * qr * (Gm[1][2] - Gm[2][1]) - 4.f * qx * (Gm[2][2] + Gm[1][1]);
                 dq.z = 2.f * qx * (Gm[1][0] + Gm[0][1]) + 2.f * qr * (Gm[2][0] - Gm[0][2]) + 2.f * qz * (Gm[1][2] + Gm[2][1]) - 4.f * qy * (Gm[2][2] + Gm[0][0]);
                 dq.w = 2.f * qr * (Gm[0][1] - Gm[1][0]) + 2.f * qx * (Gm[2][0] + Gm[0][2]) + 2.f * qy * (Gm[1][2] + Gm[2][1]) - 4.f * qz * (Gm[1][1] + Gm[0][0]);
+                if (kRaw) {                                                   // d normalize(x) = (g - q (q.g)) / |x|
+                    const float qg = qr * dq.x + qx * dq.y + qy * dq.z + qz * dq.w;
+                    const float inv = 1.0f / qnorm;
+                    dq.x = (dq.x - qr * qg) * inv; dq.y = (dq.y - qx * qg) * inv; dq.z = (dq.z - qy * qg) * inv; dq.w = (dq.w - qz * qg) * inv;
+                }
                 reinterpret_cast<float4*>(p.dL_drotations)[i] = dq;
             }
         } else if (p.dL_dcov3D) {
@@ -297,7 +335,12 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
         const size_t o3 = (size_t)i * 3;
         p.dL_dmeans3D[o3] = dmean.x; p.dL_dmeans3D[o3 + 1] = dmean.y; p.dL_dmeans3D[o3 + 2] = dmean.z;
         p.dL_dmeans2D[o3] = dmean2D_x; p.dL_dmeans2D[o3 + 1] = dmean2D_y; p.dL_dmeans2D[o3 + 2] = 0.f;
-        p.dL_dopacity[i] = dopacity;
+        if (kRaw) {                                                          // d sigmoid(x) = o (1 - o) dx; o as the forward stored it
+            const float o = __ldg(reinterpret_cast<const float*>(p.rec + (size_t)i * 3 + 1) + 1);
+            p.dL_dopacity[i] = dopacity * o * (1.0f - o);
+        } else {
+            p.dL_dopacity[i] = dopacity;
+        }
     }
 
     // ---- pose gradient: warp shuffle -> CTA -> 6 atomics ------------------------------------------------------
@@ -326,18 +369,21 @@ int launch_gaussian_backward(const G4RFrame& f, const G4RGaussians& g, const int
     p.focal_x = (float)f.width / (2.0f * f.tan_fovx);
     p.focal_y = (float)f.height / (2.0f * f.tan_fovy);
     p.scale_modifier = f.scale_modifier;
-    p.means3D = g.means3D; p.shs = g.shs; p.colors_precomp = g.colors_precomp; p.scales = g.scales; p.rotations = g.rotations;
-    p.cov3D_precomp = g.cov3D_precomp;
+    p.means3D = g.means3D; p.shs = g.shs; p.shs_rest = g.shs_rest; p.colors_precomp = g.colors_precomp; p.scales = g.scales;
+    p.rotations = g.rotations; p.cov3D_precomp = g.cov3D_precomp;
+    p.scale_dim = g.scale_dim == 1 ? 1 : 3;
     p.viewmatrix = f.viewmatrix; p.projmatrix = f.projmatrix; p.projmatrix_raw = f.projmatrix_raw; p.campos = f.campos;
     p.radii = radii;
     p.rec = (const float4*)((const char*)geom + gl.rec);
     p.clamped = (const uint8_t*)((const char*)geom + gl.clamped);
     p.acc = acc;
     p.dL_dmeans3D = io.dL_dmeans3D; p.dL_dmeans2D = io.dL_dmeans2D; p.dL_dopacity = io.dL_dopacity; p.dL_dshs = io.dL_dshs;
+    p.dL_dshs_rest = io.dL_dshs_rest;
     p.dL_dcolors_precomp = io.dL_dcolors_precomp; p.dL_dscales = io.dL_dscales; p.dL_drotations = io.dL_drotations;
     p.dL_dcov3D = io.dL_dcov3D; p.dL_dtau = io.dL_dtau;
     g4r_stage_begin(ST_GAUSSIAN_BWD, s);
-    gaussian_backward_kernel<<<(g.P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(p);
+    if (g.activation == G4R_ACT_RAW) gaussian_backward_kernel<true><<<(g.P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(p);
+    else gaussian_backward_kernel<false><<<(g.P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(p);
     g4r_stage_end(ST_GAUSSIAN_BWD, s);
     G4R_LAUNCH_OK("gaussian_backward_kernel");
     return G4R_OK;

@@ -20,7 +20,8 @@ struct ProjectParams {
     int P, D, M, W, H;
     uint32_t gx, gy;
     float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
-    const float *means3D, *opacities, *shs, *colors_precomp, *scales, *rotations, *cov3D_precomp;
+    const float *means3D, *opacities, *shs, *shs_rest, *colors_precomp, *scales, *rotations, *cov3D_precomp;
+    int scale_dim;                // raw mode: 1 = isotropic _scaling [P,1]
     const float *viewmatrix, *projmatrix, *campos;
     float4* rec;
     uint8_t* clamped;
@@ -61,7 +62,8 @@ static __device__ __forceinline__ void stage_rows3(float* s_dst, const float* __
     }
 }
 
-template <bool kVec>
+// kRaw: the inputs are GaussianModel's raw parameters (G4R_ACT_RAW); the activations are applied right after the loads.
+template <bool kVec, bool kRaw = false>
 __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams p) {
     __shared__ __align__(16) float s_mean[G4R_BLOCK * 3];
     __shared__ __align__(16) float s_aux[G4R_BLOCK * 3];   // scales
@@ -69,8 +71,9 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     const int i = row0 + threadIdx.x;
     const bool has_scale = p.cov3D_precomp == nullptr;
 
+    const bool iso = kRaw && p.scale_dim == 1;
     stage_rows3<kVec>(s_mean, p.means3D, row0, p.P);
-    if (has_scale) stage_rows3<kVec>(s_aux, p.scales, row0, p.P);
+    if (has_scale && !iso) stage_rows3<kVec>(s_aux, p.scales, row0, p.P);
     __syncthreads();
     if (i >= p.P) return;
     p.n_touched[i] = 0;                          // accumulated by composite_forward_kernel
@@ -98,9 +101,13 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     // ---- 3D covariance (forward.cu:120-154), or the precomputed one (forward.cu:207-215) --------
     float c0, c1, c2, c3, c4, c5;
     if (has_scale) {
-        const float sx = __fmul_rn(p.scale_modifier, s_aux[threadIdx.x * 3 + 0]);
-        const float sy = __fmul_rn(p.scale_modifier, s_aux[threadIdx.x * 3 + 1]);
-        const float sz = __fmul_rn(p.scale_modifier, s_aux[threadIdx.x * 3 + 2]);
+        float s0 = iso ? __ldg(p.scales + i) : s_aux[threadIdx.x * 3 + 0];
+        float s1 = iso ? s0 : s_aux[threadIdx.x * 3 + 1];
+        float s2 = iso ? s0 : s_aux[threadIdx.x * 3 + 2];
+        if (kRaw) { s0 = expf(s0); s1 = iso ? s0 : expf(s1); s2 = iso ? s0 : expf(s2); }     // scaling_activation = exp
+        const float sx = __fmul_rn(p.scale_modifier, s0);
+        const float sy = __fmul_rn(p.scale_modifier, s1);
+        const float sz = __fmul_rn(p.scale_modifier, s2);
         float qr, qx, qy, qz;                        // (r,x,y,z), NOT normalised (forward.cu:129)
         if (kVec) {
             const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + i);
@@ -108,6 +115,10 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
         } else {
             const float* q = p.rotations + (size_t)i * 4;
             qr = __ldg(q + 0); qx = __ldg(q + 1); qy = __ldg(q + 2); qz = __ldg(q + 3);
+        }
+        if (kRaw) {                                  // rotation_activation = normalize
+            const float n = g4r_quat_norm(qr, qx, qy, qz);
+            qr = __fdiv_rn(qr, n); qx = __fdiv_rn(qx, n); qy = __fdiv_rn(qy, n); qz = __fdiv_rn(qz, n);
         }
         const float yy = __fmul_rn(qy, qy), zz = __fmul_rn(qz, qz);
         const float xz = __fmul_rn(qx, qz), rz = __fmul_rn(qr, qz), rx = __fmul_rn(qr, qx);
@@ -196,8 +207,10 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
         float dx = x - __ldg(p.campos + 0), dy = y - __ldg(p.campos + 1), dz = z - __ldg(p.campos + 2);
         const float len = sqrtf(dx * dx + dy * dy + dz * dz);
         dx = dx / len; dy = dy / len; dz = dz / len;
-        const float* sh = p.shs + (size_t)i * p.M * 3;
-#define SH(k, c) __ldg(sh + (k) * 3 + (c))
+        // raw mode: coefficient 0 lives in _features_dc [P,1,3], the others in _features_rest [P,M-1,3]
+        const float* sh = kRaw ? p.shs + (size_t)i * 3 : p.shs + (size_t)i * p.M * 3;
+        const float* shr = (kRaw && p.M > 1) ? p.shs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : sh;
+#define SH(k, c) __ldg(((k) == 0 ? sh : shr) + (k) * 3 + (c))
         float col[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     // The composite kernels minimise q over a warp's 8x4 pixel patch and skip the splat when the minimum exceeds
     // cull_q; the small padding absorbs float rounding of the per-pixel evaluation, so a skipped (warp, splat)
     // pair is always one the reference would have evaluated to alpha < 1/255 for all 32 pixels.
-    const float o = __ldg(p.opacities + i);
+    const float o = kRaw ? g4r_sigmoid(__ldg(p.opacities + i)) : __ldg(p.opacities + i);   // opacity_activation = sigmoid
     float cull_q = CUDART_INF_F;                    // no culling (degenerate conic / NaN)
     if (o < (1.0f / 255.0f)) {
         cull_q = -1.0f;                             // alpha = o*exp(power<=0) < 1/255 everywhere
@@ -264,8 +277,9 @@ int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* i
     p.focal_x = (float)f.width / (2.0f * f.tan_fovx);
     p.focal_y = (float)f.height / (2.0f * f.tan_fovy);
     p.scale_modifier = f.scale_modifier;
-    p.means3D = g.means3D; p.opacities = g.opacities; p.shs = g.shs; p.colors_precomp = g.colors_precomp;
+    p.means3D = g.means3D; p.opacities = g.opacities; p.shs = g.shs; p.shs_rest = g.shs_rest; p.colors_precomp = g.colors_precomp;
     p.scales = g.scales; p.rotations = g.rotations; p.cov3D_precomp = g.cov3D_precomp;
+    p.scale_dim = g.scale_dim == 1 ? 1 : 3;
     p.viewmatrix = f.viewmatrix; p.projmatrix = f.projmatrix; p.campos = f.campos;
     p.rec = reinterpret_cast<float4*>((char*)geom + gl.rec);
     p.clamped = reinterpret_cast<uint8_t*>((char*)geom + gl.clamped);
@@ -273,10 +287,16 @@ int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* i
     p.n_touched = n_touched;
     p.tile_counts = img ? reinterpret_cast<uint32_t*>((char*)img + il.counts) : nullptr;
     const int blocks = (g.P + G4R_BLOCK - 1) / G4R_BLOCK;
+    const bool raw = g.activation == G4R_ACT_RAW;
     const bool vec = (((uintptr_t)g.means3D | (uintptr_t)g.scales | (uintptr_t)g.rotations) & 15u) == 0;
     g4r_stage_begin(ST_PROJECT, s);
-    if (vec) project_kernel<true><<<blocks, G4R_BLOCK, 0, s>>>(p);
-    else     project_kernel<false><<<blocks, G4R_BLOCK, 0, s>>>(p);
+    if (raw) {
+        if (vec) project_kernel<true, true><<<blocks, G4R_BLOCK, 0, s>>>(p);
+        else     project_kernel<false, true><<<blocks, G4R_BLOCK, 0, s>>>(p);
+    } else {
+        if (vec) project_kernel<true><<<blocks, G4R_BLOCK, 0, s>>>(p);
+        else     project_kernel<false><<<blocks, G4R_BLOCK, 0, s>>>(p);
+    }
     g4r_stage_end(ST_PROJECT, s);
     G4R_LAUNCH_OK("project_kernel");
     return G4R_OK;

@@ -31,6 +31,8 @@ __all__ = [
     "GaussianRasterizer",
     "rasterize_gaussians",
     "rasterize_gaussians_with_state",
+    "FusedGaussianRasterizer",
+    "rasterize_gaussians_raw",
     "captured_overflow",
     "reset_captured",
 ]
@@ -60,6 +62,7 @@ class _Gaussians(ctypes.Structure):
         ("means3D", ctypes.c_void_p), ("opacities", ctypes.c_void_p), ("shs", ctypes.c_void_p),
         ("colors_precomp", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p),
         ("cov3D_precomp", ctypes.c_void_p),
+        ("shs_rest", ctypes.c_void_p), ("activation", ctypes.c_int32), ("scale_dim", ctypes.c_int32),
     ]
 
 
@@ -76,6 +79,7 @@ class _BackwardIO(ctypes.Structure):
         ("dL_dmeans3D", ctypes.c_void_p), ("dL_dmeans2D", ctypes.c_void_p), ("dL_dopacity", ctypes.c_void_p),
         ("dL_dshs", ctypes.c_void_p), ("dL_dcolors_precomp", ctypes.c_void_p), ("dL_dscales", ctypes.c_void_p),
         ("dL_drotations", ctypes.c_void_p), ("dL_dcov3D", ctypes.c_void_p), ("dL_dtau", ctypes.c_void_p),
+        ("dL_dshs_rest", ctypes.c_void_p),
     ]
 
 
@@ -131,8 +135,8 @@ def _load_library() -> ctypes.CDLL:
     if list(sizes) != mine:
         raise ImportError(f"diff_gaussian_rasterization: struct layout mismatch between libg4r.so {list(sizes)} and the Python "
                           f"bindings {mine}; rebuild the library")
-    if lib.g4r_version() != 3:
-        raise ImportError(f"diff_gaussian_rasterization: libg4r.so has ABI version {lib.g4r_version()}, expected 3; rebuild it")
+    if lib.g4r_version() != 4:
+        raise ImportError(f"diff_gaussian_rasterization: libg4r.so has ABI version {lib.g4r_version()}, expected 4; rebuild it")
     return lib
 
 
@@ -216,12 +220,17 @@ def _make_frame(rs: "GaussianRasterizationSettings", device: torch.device, sh_co
     return f
 
 
-def _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp) -> _Gaussians:
+def _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw=None) -> _Gaussians:
+    """`raw` = None (reference surface: activated parameters) or (features_rest | None, scale_dim): include/g4r.h G4R_ACT_RAW."""
     g = _Gaussians()
     g.P = P
     g.means3D, g.opacities = _ptr(means3D), _ptr(opacities)
     g.shs, g.colors_precomp = _ptr(sh), _ptr(colors_precomp)
     g.scales, g.rotations, g.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3Ds_precomp)
+    if raw is not None:
+        g.activation = 1
+        g.shs_rest = _ptr(raw[0])
+        g.scale_dim = int(raw[1])
     return g
 
 
@@ -234,7 +243,9 @@ def _layout(P: int, W: int, H: int, cap: int) -> _Layout:
 # ----------------------------------------------------------------------------------------------
 # forward / backward drivers
 # ----------------------------------------------------------------------------------------------
-def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, raw=None):
+    """`raw` = None, or (features_rest tensor | None, scale_dim) when the tensors are GaussianModel's raw parameters
+    (then `sh` is _features_dc [P,1,3])."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:58-60
     if not means3D.is_cuda:
@@ -251,6 +262,14 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
     rotations = _dev_f32(rotations, device) if rotations.numel() else rotations
     cov3Ds_precomp = _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp
     M = int(sh.size(1)) if sh.numel() else 0                                    # rasterize_points.cu:87-91
+    if raw is not None:
+        rest = raw[0]
+        if rest is not None and rest.numel():
+            rest = _dev_f32(rest, device)
+            M = 1 + int(rest.size(1))
+        else:
+            rest = None
+        raw = (rest, raw[1])
 
     f32 = dict(dtype=torch.float32, device=device)
     i32 = dict(dtype=torch.int32, device=device)
@@ -274,7 +293,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         ctx = _context(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         frame = _make_frame(rs, device, M, keep)
-        g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+        g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw)
         out = _ForwardOut(color.data_ptr(), depth.data_ptr(), opacity.data_ptr(), radii.data_ptr(), n_touched.data_ptr())
 
         if torch.cuda.is_current_stream_capturing():
@@ -289,6 +308,8 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             _check(_lib.g4r_forward_render(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                            binning.data_ptr(), cap, ctypes.byref(out), stream))
             _captured.append((img, cap, _layout(P, W, H, cap).img_header))
+            if raw is not None and raw[0] is not None:
+                keep.append(raw[0])
             state = dict(P=P, N=-1, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
             return color, radii, depth, opacity, n_touched, state
 
@@ -312,28 +333,37 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                            binning.data_ptr(), cap, ctypes.byref(out), stream))
         _cap_hint[key] = max(N, int(hint * 0.95))
+    if raw is not None and raw[0] is not None:
+        keep.append(raw[0])
     state = dict(P=P, N=N, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
     return color, radii, depth, opacity, n_touched, state
 
 
 def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii, geom, img, binning,
-                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None):
+                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None, raw=None):
+    """`raw` = None or (features_rest | None, scale_dim, raw opacities): gradients are then w.r.t. the raw parameters and a
+    tenth element, the gradient of features_rest, is appended to the returned tuple."""
     device = means3D.device
     H, W = int(rs.image_height), int(rs.image_width)
     f32 = dict(dtype=torch.float32, device=device)
     M = int(sh.size(1)) if sh.numel() else 0
+    grad_rest = None
+    if raw is not None and raw[0] is not None:
+        M = 1 + int(raw[0].size(1))
+        grad_rest = torch.empty((P, M - 1, 3), **f32)
     tau = torch.empty((8,), **f32)
     grad_means3D = torch.empty((P, 3), **f32)
     grad_means2D = torch.empty((P, 3), **f32)
     grad_opacities = torch.empty(opacities_shape, **f32)
-    grad_sh = torch.empty((P, M, 3), **f32) if sh.numel() else None
+    grad_sh = torch.empty((P, 1 if raw is not None else M, 3), **f32) if sh.numel() else None
     grad_colors = torch.empty((P, 3), **f32) if colors_precomp.numel() else None
-    grad_scales = torch.empty((P, 3), **f32) if scales.numel() else None
+    grad_scales = torch.empty((P, raw[1] if raw is not None else 3), **f32) if scales.numel() else None
     grad_rot = torch.empty((P, 4), **f32) if rotations.numel() else None
     grad_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp.numel() else None
     if P == 0:
         tau.zero_()
-        return grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau
+        res = (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau)
+        return res + (grad_rest,) if raw is not None else res
 
     grad_out_color = _dev_f32(grad_out_color, device)
     grad_out_depth = _dev_f32(grad_out_depth, device)
@@ -344,14 +374,16 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
         frame, keep = frame_keep if frame_keep is not None else (None, [])
         if frame is None:
             frame = _make_frame(rs, device, M, keep)
-        g = _make_gaussians(P, means3D, None, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+        g = _make_gaussians(P, means3D, None, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
+                            None if raw is None else (raw[0], raw[1]))
         g.opacities = means3D.data_ptr()   # opacities are not read in backward (they live in the splat records)
         io = _BackwardIO(grad_out_color.data_ptr(), grad_out_depth.data_ptr(), grad_means3D.data_ptr(), grad_means2D.data_ptr(),
                          grad_opacities.data_ptr(), _ptr(grad_sh), _ptr(grad_colors), _ptr(grad_scales), _ptr(grad_rot),
-                         _ptr(grad_cov), tau.data_ptr())
+                         _ptr(grad_cov), tau.data_ptr(), _ptr(grad_rest))
         _check(_lib.g4r_backward(ctypes.byref(frame), ctypes.byref(g), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
                                  binning.data_ptr(), scratch.data_ptr(), ctypes.byref(io), stream))
-    return grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau
+    res = (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau)
+    return res + (grad_rest,) if raw is not None else res
 
 
 # ----------------------------------------------------------------------------------------------
@@ -487,6 +519,86 @@ class GaussianRasterizer(nn.Module):
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                                    theta, rho, raster_settings)
+
+
+# ----------------------------------------------------------------------------------------------
+# opt-in extension: raw-parameter rasterizer ("render() prelude fusion")
+# ----------------------------------------------------------------------------------------------
+class _RasterizeGaussiansRaw(torch.autograd.Function):
+    """Same op as `_RasterizeGaussians`, but the inputs are `GaussianModel`'s raw parameters
+    (`_xyz, _features_dc, _features_rest, _opacity, _scaling, _rotation`); the activations of
+    `gaussian_splatting/scene/gaussian_model.py:100-128` (sigmoid / exp / normalize / cat) run inside the projection kernel and
+    their chain rule inside the per-Gaussian backward kernel, so the ~7 element-wise torch kernels of the prelude of
+    `gaussian_renderer/__init__.py:108-131` and their autograd twins disappear."""
+
+    @staticmethod
+    def forward(ctx, xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta, rho, raster_settings):
+        e = _empty()
+        scale_dim = int(scaling_raw.size(1)) if scaling_raw.dim() == 2 else 0
+        if scale_dim not in (1, 3):
+            raise RuntimeError("scaling_raw must have dimensions (num_points, 3) or (num_points, 1)")
+        if features_dc.dim() != 3 or features_dc.size(1) != 1 or features_dc.size(2) != 3:
+            raise RuntimeError("features_dc must have dimensions (num_points, 1, 3)")
+        color, radii, depth, opacity, n_touched, state = _forward_impl(
+            xyz, features_dc, e, opacity_raw, scaling_raw, rotation_raw, e, raster_settings, raw=(features_rest, scale_dim))
+        ctx.raster_settings = raster_settings
+        ctx.P = state["P"]
+        ctx.scale_dim = scale_dim
+        ctx.opacities_shape = tuple(opacity_raw.shape)
+        ctx.frame_keep = state.get("frame")
+        ctx.save_for_backward(xyz, features_dc, features_rest, scaling_raw, rotation_raw, radii,
+                              state["geom"], state["binning"], state["img"])
+        ctx.mark_non_differentiable(radii, n_touched)
+        return color, radii, depth, opacity, n_touched
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_radii, grad_out_depth, grad_out_opacity, grad_n_touched):
+        xyz, features_dc, features_rest, scaling_raw, rotation_raw, radii, geom, binning, img = ctx.saved_tensors
+        device = xyz.device
+        e = _empty()
+        rest = _dev_f32(features_rest, device) if features_rest.numel() else None
+        (g_xyz, g_m2d, g_dc, _gc, g_op, g_sc, g_rot, _gcov, tau, g_rest) = _backward_impl(
+            ctx.raster_settings, ctx.P, _dev_f32(xyz, device), _dev_f32(features_dc, device), e, _dev_f32(scaling_raw, device),
+            _dev_f32(rotation_raw, device), e, radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth,
+            ctx.frame_keep, raw=(rest, ctx.scale_dim))
+        if g_rest is None and features_rest.numel() == 0 and ctx.needs_input_grad[3]:
+            g_rest = torch.zeros_like(features_rest)
+        needs = ctx.needs_input_grad
+        return (g_xyz, g_m2d, g_dc, g_rest, g_op, g_sc, g_rot,
+                tau[3:6].view(1, -1) if needs[7] else None, tau[:3].view(1, -1) if needs[8] else None, None)
+
+
+def rasterize_gaussians_raw(xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta, rho,
+                            raster_settings):
+    return _RasterizeGaussiansRaw.apply(xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw,
+                                        theta, rho, raster_settings)
+
+
+class FusedGaussianRasterizer(nn.Module):
+    """`GaussianRasterizer` fed with the model's raw parameters.  In `render()` it replaces
+
+        rasterizer(means3D=pc.get_xyz, means2D=..., shs=pc.get_features, opacities=pc.get_opacity,
+                   scales=pc.get_scaling, rotations=pc.get_rotation, theta=..., rho=...)
+    by
+        FusedGaussianRasterizer(raster_settings)(xyz=pc._xyz, means2D=..., features_dc=pc._features_dc,
+                   features_rest=pc._features_rest, opacity_raw=pc._opacity, scaling_raw=pc._scaling,
+                   rotation_raw=pc._rotation, theta=..., rho=...)
+
+    and returns the same 5-tuple; gradients arrive directly on the raw parameters."""
+
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def forward(self, xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta=None, rho=None):
+        if features_rest is None:
+            features_rest = _empty()
+        if theta is None:
+            theta = _empty()
+        if rho is None:
+            rho = _empty()
+        return rasterize_gaussians_raw(xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw,
+                                       theta, rho, self.raster_settings)
 
 
 # ----------------------------------------------------------------------------------------------

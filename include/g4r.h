@@ -47,6 +47,9 @@ extern "C" {
 #define G4R_ECUDA        -2   /* a CUDA runtime call or kernel launch failed            */
 #define G4R_EOVERFLOW    -3   /* binning capacity too small (informational)              */
 
+#define G4R_ACT_NONE      0   /* inputs are activated parameters (the reference rasterizer's contract) */
+#define G4R_ACT_RAW       1   /* inputs are GaussianModel's raw parameters; activations are applied in-kernel */
+
 #define G4R_TILE          16  /* tile edge in pixels: BLOCK_X/BLOCK_Y of DGR/cuda_rasterizer/config.h:16-17 */
 #define G4R_CHANNELS      3   /* NUM_CHANNELS of DGR/cuda_rasterizer/config.h:15 */
 
@@ -87,6 +90,18 @@ typedef struct G4RGaussians {
     const float* scales;          /* [P,3] (post-exp)  or NULL */
     const float* rotations;       /* [P,4] (w,x,y,z)   or NULL */
     const float* cov3D_precomp;   /* [P,6] or NULL  (exactly one of scales+rotations / cov3D_precomp) */
+    /* ---- raw-parameter mode (opt-in; folds the activation prelude of the caller into the kernels) ----------------
+     * The reference's render() (gaussian_splatting/gaussian_renderer/__init__.py:108-131) feeds the rasterizer
+     * GaussianModel.get_opacity = sigmoid(_opacity), get_scaling = exp(_scaling) (repeated x3 when isotropic),
+     * get_rotation = normalize(_rotation) and get_features = cat(_features_dc, _features_rest)
+     * (gaussian_splatting/scene/gaussian_model.py:100-128): ~7 element-wise torch kernels per call plus their
+     * autograd twins.  With activation = G4R_ACT_RAW the pointers above are the RAW parameters: opacities = _opacity,
+     * scales = _scaling [P,scale_dim], rotations = _rotation, shs = _features_dc [P,1,3], shs_rest = _features_rest
+     * [P,M-1,3] (NULL when M == 1); the kernels apply the activations, and the backward returns gradients w.r.t. the
+     * raw parameters (chain rule of exp / sigmoid / normalize applied in the per-Gaussian backward kernel). */
+    const float* shs_rest;        /* [P,M-1,3] or NULL; only read when activation == G4R_ACT_RAW */
+    int32_t activation;           /* G4R_ACT_NONE (reference surface) or G4R_ACT_RAW */
+    int32_t scale_dim;            /* raw mode: 3, or 1 for an isotropic _scaling [P,1]; 0 means 3 */
 } G4RGaussians;
 
 /* Forward outputs (DEVICE pointers, written in full; no pre-zeroing needed). */
@@ -113,13 +128,14 @@ typedef struct G4RBackwardIO {
     float* dL_drotations;         /* [P,4]   or NULL */
     float* dL_dcov3D;             /* [P,6]   or NULL (only when cov3D_precomp was given) */
     float* dL_dtau;               /* [8]: [0:3] = grad_rho, [3:6] = grad_theta, [6:8] padding */
+    float* dL_dshs_rest;          /* [P,M-1,3] or NULL; raw mode only (then dL_dshs is [P,1,3], dL_dscales [P,scale_dim]) */
 } G4RBackwardIO;
 
 typedef struct G4RContext G4RContext;   /* owns one pinned int + one event; one per host thread/device */
 
 /* ---- library / context ------------------------------------------------------------ */
 const char* g4r_last_error(void);
-int  g4r_version(void);                               /* ABI version, currently 3 */
+int  g4r_version(void);                               /* ABI version, currently 4 */
 void g4r_struct_sizes(int32_t* out5);                 /* sizeof {G4RFrame, G4RGaussians, G4RForwardOut, G4RBackwardIO, G4RLayout}: FFI self-check */
 int  g4r_context_create(G4RContext** out);
 void g4r_context_destroy(G4RContext* ctx);

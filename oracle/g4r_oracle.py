@@ -171,3 +171,40 @@ class Oracle:
 def scene_dict(scene) -> dict:
     """tools.scenes.Scene -> plain dict understood by Oracle.forward."""
     return dict(scene.__dict__)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Raw-parameter mode (include/g4r.h G4R_ACT_RAW; SURVEY.md section 8f-1).  Restates the activation prelude of the
+# reference's render() (gaussian_splatting/gaussian_renderer/__init__.py:108-131 with
+# gaussian_splatting/scene/gaussian_model.py:100-128: get_scaling = exp, get_opacity = sigmoid, get_rotation = normalize,
+# get_features = cat(dc, rest)) and the chain rule autograd applies to it, in numpy.  Pinned by
+# tests/test_raw_activation.py against torch's own autograd through exactly those torch calls.
+# ---------------------------------------------------------------------------------------------------------------------
+def activate_raw(opacity_raw, features_dc, features_rest, scaling_raw, rotation_raw, dtype=np.float32) -> dict:
+    """Raw GaussianModel parameters -> the activated tensors the reference rasterizer receives."""
+    f = lambda a: None if a is None else np.asarray(a, dtype=dtype)
+    o, dc, rest, s, q = f(opacity_raw), f(features_dc), f(features_rest), f(scaling_raw), f(rotation_raw)
+    one = dtype(1.0)
+    scales = np.exp(s)
+    if scales.shape[1] == 1:
+        scales = np.repeat(scales, 3, axis=1)
+    # |q|^2 accumulated r, x, y, z with one rounding per step, like g4r_quat_norm (fma chain) up to the fma's single rounding
+    n = np.maximum(np.sqrt((q.astype(np.float64) ** 2).sum(1)).astype(dtype), dtype(1e-12))[:, None]
+    return dict(opacities=(one / (one + np.exp(-o))).astype(dtype), scales=scales.astype(dtype), rotations=(q / n).astype(dtype),
+                shs=dc if rest is None or rest.shape[1] == 0 else np.concatenate([dc, rest], axis=1), rot_norm=n)
+
+
+def raw_chain_rule(act: dict, grads: dict, scale_dim: int = 3) -> dict:
+    """Gradients w.r.t. the activated tensors (Oracle.backward output) -> gradients w.r.t. the raw parameters."""
+    o = act["opacities"].reshape(-1).astype(np.float64)
+    s = act["scales"].astype(np.float64)
+    q = act["rotations"].astype(np.float64)
+    n = act["rot_norm"].astype(np.float64)
+    gs = grads["dL_dscales"].astype(np.float64) * s
+    if scale_dim == 1:
+        gs = gs.sum(1, keepdims=True)
+    gq = grads["dL_drots"].astype(np.float64)
+    gq = (gq - q * (q * gq).sum(1, keepdims=True)) / n
+    gsh = grads["dL_dshs"]
+    return dict(dL_dopacity_raw=grads["dL_dopacity"].astype(np.float64).reshape(-1) * o * (1.0 - o), dL_dscaling_raw=gs,
+                dL_drotation_raw=gq, dL_dfeatures_dc=gsh[:, :1], dL_dfeatures_rest=gsh[:, 1:])

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_sizes():
     lib = ctypes.CDLL(LIB)
-    assert lib.g4r_version() == 3
+    assert lib.g4r_version() == 4
     for f in (lib.g4r_geom_bytes, lib.g4r_binning_bytes, lib.g4r_backward_scratch_bytes, lib.g4r_image_bytes):
         f.restype = ctypes.c_size_t
     lib.g4r_geom_bytes.argtypes = [ctypes.c_int32]

@@ -297,6 +297,61 @@ def test_forward_is_deterministic(device):
     assert bool((a["opacity"][0] == 1.0 - a["final_T"]).all())
 
 
+def _l2rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("deg,M,scale_dim", [(1, 4, 3), (0, 1, 3), (3, 16, 3), (1, 4, 1)])
+def test_fused_raw_parameters_match_torch_prelude(device, deg, M, scale_dim):
+    """FusedGaussianRasterizer (activations + their chain rule inside the kernels) against the reference's
+    prelude -- torch.sigmoid / exp / normalize / cat (gaussian_model.py:100-128) feeding the standard rasterizer.  exp and
+    sigmoid are reproduced bit for bit; normalize may differ in the last bit, hence tolerances instead of equality:
+    images 1e-4 of peak (BASELINE.json), gradients 1e-3 relative L2."""
+    import diff_gaussian_rasterization as dgr
+    sc = make_scene(20000, 320, 240, sh_degree=deg, sh_coeffs=M, seed=100 + M + scale_dim).to(device)
+    raw = runners.raw_parameters(sc, scale_dim=scale_dim, seed=5)
+    a = runners.run_raw(sc, dgr, raw, fused=True)
+    b = runners.run_raw(sc, dgr, raw, fused=False)
+    assert int((a["radii"] != b["radii"]).sum()) <= 2
+    assert int((a["n_touched"] != b["n_touched"]).sum()) <= max(4, sc.P // 2000)
+    for k in ("color", "depth", "opacity"):
+        tol = 1e-4 * max(1.0, float(b[k].abs().max()))
+        bad = (a[k] - b[k]).abs() > tol
+        assert float(bad.float().mean()) < 1e-4, (k, float((a[k] - b[k]).abs().max()))       # a threshold flip may move a few pixels
+    for k in ("g_xyz", "g_opacity", "g_scaling", "g_rotation", "g_dc", "g_rest", "dL_dmeans2D", "dL_dtau"):
+        if b[k] is None or b[k].numel() == 0:
+            assert a[k] is None or a[k].numel() == 0 or float(a[k].abs().max()) == 0.0, k
+            continue
+        assert a[k].shape == b[k].shape, k
+        assert _l2rel(a[k], b[k]) < 1e-3, (k, _l2rel(a[k], b[k]))
+
+
+def test_fused_raw_parameters_match_oracle(device):
+    """The same extension against the CPU restatement: oracle forward/backward on the numpy-activated parameters, then the
+    numpy chain rule (oracle.g4r_oracle.activate_raw / raw_chain_rule, pinned to torch autograd by tests/test_raw_activation.py)."""
+    import diff_gaussian_rasterization as dgr
+    from oracle.g4r_oracle import Oracle, activate_raw, raw_chain_rule, scene_dict
+    sc_cpu = make_scene(3000, 160, 120, sh_degree=2, seed=131)
+    sc = sc_cpu.to(device)
+    raw = runners.raw_parameters(sc, seed=6)
+    a = runners.run_raw(sc, dgr, raw, fused=True)
+    n = {k: v.cpu().numpy() for k, v in raw.items()}
+    act = activate_raw(n["opacity"], n["dc"], n["rest"], n["scaling"], n["rotation"])
+    d = scene_dict(sc_cpu)
+    d.update(opacities=torch.from_numpy(act["opacities"]), scales=torch.from_numpy(act["scales"]),
+             rotations=torch.from_numpy(act["rotations"]), shs=torch.from_numpy(np.ascontiguousarray(act["shs"])))
+    ora = Oracle("f32")
+    f = ora.forward(d)
+    g = raw_chain_rule(act, ora.backward(f, sc_cpu.grad_color, sc_cpu.grad_depth))
+    assert int((a["radii"].cpu().numpy() != f["radii"]).sum()) <= 1
+    assert np.abs(a["color"].cpu().numpy() - f["color"]).max() < 1e-4
+    for mine, ref in (("g_opacity", "dL_dopacity_raw"), ("g_scaling", "dL_dscaling_raw"), ("g_rotation", "dL_drotation_raw"),
+                      ("g_dc", "dL_dfeatures_dc"), ("g_rest", "dL_dfeatures_rest")):
+        x, y = a[mine].cpu().numpy().reshape(-1).astype(np.float64), np.asarray(g[ref], np.float64).reshape(-1)
+        assert np.linalg.norm(x - y) / (np.linalg.norm(y) + 1e-30) < 2e-3, mine
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sharded_render_two_gpus(tmp_path):
     """Gaussian-sharded render on 2 GPUs (NCCL) == single-GPU render: bit-identical images, gradients to 1e-4."""

@@ -36,6 +36,7 @@ for stage in "$@"; do
     hostline) timeout 600 python tools/host_timeline.py > gpurun_out/host_timeline.log 2>&1; echo "rc=$?"; cut -c1-1200 gpurun_out/host_timeline.log ;;
     determinism) timeout 900 python tools/determinism_check.py > gpurun_out/determinism.log 2>&1; echo "rc=$?"; cut -c1-2500 gpurun_out/determinism.log ;;
     repro)    timeout 900 python tools/repro_anomaly.py 16 > gpurun_out/repro_anomaly.log 2>&1; echo "rc=$?"; cut -c1-1500 gpurun_out/repro_anomaly.log ;;
+    prelude)  timeout 600 python tools/prelude_bench.py > gpurun_out/prelude_bench.log 2>&1; echo "rc=$?"; cut -c1-700 gpurun_out/prelude_bench.log ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

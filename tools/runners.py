@@ -129,3 +129,51 @@ def fmt_report(rep: dict) -> str:
     for k, v in rep.items():
         lines.append(f"    {k:14s} {v}")
     return "\n".join(lines)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# raw-parameter mode (FusedGaussianRasterizer) helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def raw_parameters(sc, scale_dim: int = 3, seed: int = 0) -> dict:
+    """GaussianModel-style raw parameters whose activations reproduce the scene: _opacity = logit, _scaling = log (the mean
+    log-scale when isotropic), _rotation = the unit quaternion times a random length, SH split into dc / rest."""
+    g = torch.Generator().manual_seed(seed)
+    P = sc.P
+    dev = sc.means3D.device
+    o = sc.opacities.double().clamp(1e-6, 1 - 1e-6)
+    length = (0.25 + 3.75 * torch.rand(P, 1, generator=g, dtype=torch.float64)).to(dev)
+    scaling = torch.log(sc.scales.double())
+    if scale_dim == 1:
+        scaling = scaling.mean(1, keepdim=True)
+    return dict(xyz=sc.means3D.clone(), opacity=torch.log(o / (1 - o)).float(), scaling=scaling.float(),
+                rotation=(sc.rotations.double() * length).float(), dc=sc.shs[:, :1].contiguous().clone(),
+                rest=sc.shs[:, 1:].contiguous().clone())
+
+
+def run_raw(sc, dgr, raw: dict, fused: bool) -> dict:
+    """fwd+bwd on the raw parameters: `fused` -> FusedGaussianRasterizer; else the reference's torch prelude
+    (gaussian_model.py:100-128) followed by the standard GaussianRasterizer."""
+    rs = settings_for(sc, dgr)
+    dev = sc.means3D.device
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+    m2d = torch.zeros_like(leaf["xyz"], requires_grad=True)
+    theta = torch.zeros(3, device=dev, requires_grad=True)
+    rho = torch.zeros(3, device=dev, requires_grad=True)
+    if fused:
+        out = dgr.FusedGaussianRasterizer(rs)(xyz=leaf["xyz"], means2D=m2d, features_dc=leaf["dc"], features_rest=leaf["rest"],
+                                              opacity_raw=leaf["opacity"], scaling_raw=leaf["scaling"], rotation_raw=leaf["rotation"],
+                                              theta=theta, rho=rho)
+    else:
+        scal = torch.exp(leaf["scaling"])
+        if scal.shape[-1] == 1:
+            scal = scal.repeat(1, 3)
+        out = dgr.GaussianRasterizer(rs)(means3D=leaf["xyz"], means2D=m2d, opacities=torch.sigmoid(leaf["opacity"]),
+                                         shs=torch.cat((leaf["dc"], leaf["rest"]), dim=1), scales=scal,
+                                         rotations=torch.nn.functional.normalize(leaf["rotation"]), theta=theta, rho=rho)
+    color, radii, depth, opacity, n_touched = out
+    ((color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()).backward()
+    res = dict(color=color.detach(), depth=depth.detach(), opacity=opacity.detach(), radii=radii, n_touched=n_touched,
+               dL_dmeans2D=m2d.grad, dL_dtau=torch.cat([rho.grad.reshape(-1), theta.grad.reshape(-1)]))
+    for k in leaf:
+        res["g_" + k] = leaf[k].grad
+    return res
