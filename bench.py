@@ -460,6 +460,7 @@ def main():
             dom = max(kt, key=kt.get)
             ach = per_kernel[dom] / (kt[dom] * 1e-3) / 1e9
             traffic = None
+            warp_inst = None
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tpath) and args.workload == "C3":
                 # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture
@@ -468,10 +469,20 @@ def main():
                 for kname, kv in tj["kernels"].items():
                     if dom in kname or (dom == "binning" and "tile_sort" in kname):
                         traffic = kv["dram_bytes_per_launch"]
+                        warp_inst = kv.get("warp_instructions")
             line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": traffic, "algorithmic_bytes_per_launch": per_kernel[dom], "ms_per_launch": kt[dom],
                                 "peak_source": peak_src}
             line["kernel_ms"] = {k: round(v[0], 5) for k, v in stage.items()}
+            if warp_inst and clocks and clocks.get("sm_mhz"):
+                # The dominant kernel is bound by instruction issue, not by HBM: warp instructions it executes
+                # (smsp__inst_executed.sum of the committed ncu capture) per second of its live duration, against
+                # SMs x 4 schedulers x the SM clock sampled during this run.  Informational, next to the HBM roofline above.
+                n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+                peak_issue = n_sm * 4 * clocks["sm_mhz"] * 1e6
+                ach_issue = warp_inst / (kt[dom] * 1e-3)
+                line["issue_roofline"] = {"kernel": dom, "warp_instructions_per_launch": warp_inst, "achieved": ach_issue / 1e9,
+                                          "peak": peak_issue / 1e9, "unit": "G warp-instructions/s", "frac": ach_issue / peak_issue}
         if graph_ms is not None:
             line["cuda_graph"] = {"value": 1000.0 / graph_ms, "unit": "frames/s", "ms_per_step": graph_ms, "capacity_overflow": graph_overflow,
                                   "note": "same step (fwd + loss + bwd through the public API) captured once with torch.cuda.graph and replayed; "

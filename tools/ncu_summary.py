@@ -61,6 +61,8 @@ def main():
         rd = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
         wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
         traffic[name] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr}
+        if "smsp__inst_executed.sum" in idx:
+            traffic[name]["warp_instructions"] = float(r[idx["smsp__inst_executed.sum"]].replace(",", ""))
         out.append(f"| DRAM traffic per launch | {(rd + wr) / 1e6:.2f} MB |")
         out.append("")
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
