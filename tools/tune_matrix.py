@@ -15,9 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
 
 VARIANTS = {
     "default": {},
-    "backward 1 px/lane (CTA per half tile)": {"BWD_2PX": 0},
-    "backward 2 px/lane, 7 CTAs/SM": {"BWD2_MINB": 7},
-    "backward 2 px/lane, 6 CTAs/SM": {"BWD2_MINB": 6},
+    "no LPT (tiles in index order)": {"LPT": 0},
 }
 # Round-1 history (profiles/r01_v7_tune_matrix.json) also covered shapes that were measured and dropped from the source:
 # forward capped at 56 / 48 registers (9 / 10 CTAs per SM), backward CTA per tile with 64 / 128 staged splats, backward CTA
