@@ -243,7 +243,7 @@ def _layout(P: int, W: int, H: int, cap: int) -> _Layout:
 # ----------------------------------------------------------------------------------------------
 # forward / backward drivers
 # ----------------------------------------------------------------------------------------------
-def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, raw=None, want_backward=False):
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, raw=None):
     """`raw` = None, or (features_rest tensor | None, scale_dim) when the tensors are GaussianModel's raw parameters
     (then `sh` is _features_dc [P,1,3])."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
@@ -324,13 +324,6 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
         _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                        binning.data_ptr(), cap, ctypes.byref(out), stream))
-        # Everything is in the stream; before blocking on the instance count, do the host work the backward would otherwise do
-        # between this call's return and the launch of its kernels (its allocations).
-        bwd_buffers = None
-        if want_backward:
-            bwd_buffers = _backward_buffers(device, P, M, tuple(opacities.shape), bool(sh.numel()), bool(colors_precomp.numel()),
-                                            bool(scales.numel()), bool(rotations.numel()), bool(cov3Ds_precomp.numel()),
-                                            None if raw is None else raw[1])
         N = int(_lib.g4r_wait_num_rendered(ctx))
         if N < 0:
             _check(N)
@@ -342,48 +335,31 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         _cap_hint[key] = max(N, int(hint * 0.95))
     if raw is not None and raw[0] is not None:
         keep.append(raw[0])
-    state = dict(P=P, N=N, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep), bwd_buffers=bwd_buffers)
+    state = dict(P=P, N=N, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
     return color, radii, depth, opacity, n_touched, state
 
 
-def _backward_buffers(device, P, M, opacities_shape, has_sh, has_colors, has_scales, has_rot, has_cov, raw_scale_dim=None):
-    """Gradient tensors and the accumulator scratch of ONE backward call.  `raw_scale_dim` = None (reference surface) or the
-    width of the raw _scaling tensor (raw-parameter mode: SH gradients split into dc [P,1,3] and rest [P,M-1,3])."""
-    f32 = dict(dtype=torch.float32, device=device)
-    raw = raw_scale_dim is not None
-    b = dict(
-        tau=torch.empty((8,), **f32),
-        means3D=torch.empty((P, 3), **f32),
-        means2D=torch.empty((P, 3), **f32),
-        opacities=torch.empty(opacities_shape, **f32),
-        sh=torch.empty((P, 1 if raw else M, 3), **f32) if has_sh else None,
-        rest=torch.empty((P, M - 1, 3), **f32) if raw and M > 1 else None,
-        colors=torch.empty((P, 3), **f32) if has_colors else None,
-        scales=torch.empty((P, raw_scale_dim if raw else 3), **f32) if has_scales else None,
-        rot=torch.empty((P, 4), **f32) if has_rot else None,
-        cov=torch.empty((P, 6), **f32) if has_cov else None,
-        scratch=torch.empty((_lib.g4r_backward_scratch_bytes(P),), dtype=torch.uint8, device=device) if P else None,
-    )
-    return b
-
-
 def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii, geom, img, binning,
-                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None, raw=None, buffers=None):
-    """`raw` = None or (features_rest | None, scale_dim): gradients are then w.r.t. the raw parameters and a tenth element,
-    the gradient of features_rest, is appended to the returned tuple.  `buffers` = the result of `_backward_buffers` when the
-    forward already allocated them (it does so while it waits for the device, which takes them off the critical path between
-    the forward's return and the launch of the backward kernels)."""
+                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None, raw=None):
+    """`raw` = None or (features_rest | None, scale_dim, raw opacities): gradients are then w.r.t. the raw parameters and a
+    tenth element, the gradient of features_rest, is appended to the returned tuple."""
     device = means3D.device
     H, W = int(rs.image_height), int(rs.image_width)
+    f32 = dict(dtype=torch.float32, device=device)
     M = int(sh.size(1)) if sh.numel() else 0
+    grad_rest = None
     if raw is not None and raw[0] is not None:
         M = 1 + int(raw[0].size(1))
-    if buffers is None:
-        buffers = _backward_buffers(device, P, M, opacities_shape, bool(sh.numel()), bool(colors_precomp.numel()), bool(scales.numel()),
-                                    bool(rotations.numel()), bool(cov3Ds_precomp.numel()), None if raw is None else raw[1])
-    tau, grad_means3D, grad_means2D, grad_opacities = buffers["tau"], buffers["means3D"], buffers["means2D"], buffers["opacities"]
-    grad_sh, grad_rest, grad_colors = buffers["sh"], buffers["rest"], buffers["colors"]
-    grad_scales, grad_rot, grad_cov, scratch = buffers["scales"], buffers["rot"], buffers["cov"], buffers["scratch"]
+        grad_rest = torch.empty((P, M - 1, 3), **f32)
+    tau = torch.empty((8,), **f32)
+    grad_means3D = torch.empty((P, 3), **f32)
+    grad_means2D = torch.empty((P, 3), **f32)
+    grad_opacities = torch.empty(opacities_shape, **f32)
+    grad_sh = torch.empty((P, 1 if raw is not None else M, 3), **f32) if sh.numel() else None
+    grad_colors = torch.empty((P, 3), **f32) if colors_precomp.numel() else None
+    grad_scales = torch.empty((P, raw[1] if raw is not None else 3), **f32) if scales.numel() else None
+    grad_rot = torch.empty((P, 4), **f32) if rotations.numel() else None
+    grad_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp.numel() else None
     if P == 0:
         tau.zero_()
         res = (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau)
@@ -391,6 +367,7 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
 
     grad_out_color = _dev_f32(grad_out_color, device)
     grad_out_depth = _dev_f32(grad_out_depth, device)
+    scratch = torch.empty((_lib.g4r_backward_scratch_bytes(P),), dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         # the forward's frame struct (camera pointers; the tensors behind them are kept alive next to it) is reused
@@ -418,22 +395,12 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                                      theta, rho, raster_settings)
 
 
-def _take_buffers(ctx):
-    """The gradient buffers the forward allocated -- usable ONCE (a second backward through a retained graph must not write
-    into tensors the first one handed to autograd)."""
-    b = getattr(ctx, "bwd_buffers", None)
-    ctx.bwd_buffers = None
-    return b
-
-
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho,
                 raster_settings):
         color, radii, depth, opacity, n_touched, state = _forward_impl(
-            means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
-            want_backward=any(ctx.needs_input_grad))
-        ctx.bwd_buffers = state.get("bwd_buffers")
+            means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
         ctx.raster_settings = raster_settings
         ctx.num_rendered = state["N"]
         ctx.P = state["P"]
@@ -458,7 +425,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _dev_f32(scales, device) if scales.numel() else scales,
             _dev_f32(rotations, device) if rotations.numel() else rotations,
             _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp,
-            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep, buffers=_take_buffers(ctx))
+            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep)
         grad_rho = tau[:3].view(1, -1)
         grad_theta = tau[3:6].view(1, -1)
         needs = ctx.needs_input_grad
@@ -573,9 +540,7 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
         if features_dc.dim() != 3 or features_dc.size(1) != 1 or features_dc.size(2) != 3:
             raise RuntimeError("features_dc must have dimensions (num_points, 1, 3)")
         color, radii, depth, opacity, n_touched, state = _forward_impl(
-            xyz, features_dc, e, opacity_raw, scaling_raw, rotation_raw, e, raster_settings, raw=(features_rest, scale_dim),
-            want_backward=any(ctx.needs_input_grad))
-        ctx.bwd_buffers = state.get("bwd_buffers")
+            xyz, features_dc, e, opacity_raw, scaling_raw, rotation_raw, e, raster_settings, raw=(features_rest, scale_dim))
         ctx.raster_settings = raster_settings
         ctx.P = state["P"]
         ctx.scale_dim = scale_dim
@@ -595,7 +560,7 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
         (g_xyz, g_m2d, g_dc, _gc, g_op, g_sc, g_rot, _gcov, tau, g_rest) = _backward_impl(
             ctx.raster_settings, ctx.P, _dev_f32(xyz, device), _dev_f32(features_dc, device), e, _dev_f32(scaling_raw, device),
             _dev_f32(rotation_raw, device), e, radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth,
-            ctx.frame_keep, raw=(rest, ctx.scale_dim), buffers=_take_buffers(ctx))
+            ctx.frame_keep, raw=(rest, ctx.scale_dim))
         if g_rest is None and features_rest.numel() == 0 and ctx.needs_input_grad[3]:
             g_rest = torch.zeros_like(features_rest)
         needs = ctx.needs_input_grad
