@@ -297,6 +297,27 @@ def test_forward_is_deterministic(device):
     assert bool((a["opacity"][0] == 1.0 - a["final_T"]).all())
 
 
+def test_two_backwards_through_a_retained_graph(device):
+    """utils/slam_backend.py:657 calls backward(retain_graph=True): a second backward through the same graph must return
+    fresh tensors and leave what the first one returned untouched."""
+    import diff_gaussian_rasterization as dgr
+    sc = make_scene(6000, 160, 120, sh_degree=1, seed=77).to(device)
+    rs = runners.settings_for(sc, dgr)
+    leaf = {k: getattr(sc, k).clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "scales", "rotations")}
+    m2d = torch.zeros_like(leaf["means3D"], requires_grad=True)
+    color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
+        means3D=leaf["means3D"], means2D=m2d, opacities=leaf["opacities"], shs=leaf["shs"], scales=leaf["scales"], rotations=leaf["rotations"])
+    loss = (color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()
+    g1 = torch.autograd.grad(loss, list(leaf.values()), retain_graph=True)
+    keep = [g.clone() for g in g1]
+    g2 = torch.autograd.grad(2.0 * loss, list(leaf.values()))
+    torch.cuda.synchronize()
+    for a, b, c in zip(g1, keep, g2):
+        assert torch.equal(a, b)                                   # untouched by the second backward
+        assert a.data_ptr() != c.data_ptr()
+        assert float((2.0 * a - c).norm() / (c.norm() + 1e-30)) < 1e-5
+
+
 def _l2rel(a, b):
     a, b = a.double(), b.double()
     return float((a - b).norm() / (b.norm() + 1e-30))
