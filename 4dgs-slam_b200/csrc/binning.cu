@@ -28,8 +28,7 @@
 // count/max).  The per-tile kernels map blockIdx.x through it, so the hardware block scheduler starts the heaviest
 // tiles first and the light ones fill the tail (longest-processing-time-first); results do not depend on it.
 __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
-                                                                 uint32_t* __restrict__ header, uint32_t* __restrict__ order,
-                                                                 uint32_t* __restrict__ sub_start, int tiles) {
+                                                                 uint32_t* __restrict__ header, uint32_t* __restrict__ order, int tiles) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_wmax[SCAN_THREADS / 32];
     __shared__ uint32_t s_bucket[ORDER_BUCKETS];
@@ -38,9 +37,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __res
     if (threadIdx.x < ORDER_BUCKETS) s_bucket[threadIdx.x] = 0;
     uint32_t sum = 0, cmax = 0;
     for (int t = t0; t < t1; ++t) {
-        uint32_t c = 0;
-#pragma unroll
-        for (int u = 0; u < G4R_COUNT_SUB; ++u) c += counts[((size_t)t * G4R_COUNT_SUB + u) * G4R_COUNT_STRIDE];
+        const uint32_t c = counts[(size_t)t * G4R_COUNT_STRIDE];
         sum += c;
         cmax = max(cmax, c);
     }
@@ -72,14 +69,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __res
     __syncthreads();
     uint32_t run = s_warp[warp] + incl - sum;
     for (int t = t0; t < t1; ++t) {
-        uint32_t c = 0;
-#pragma unroll
-        for (int u = 0; u < G4R_COUNT_SUB; ++u) {
-            uint32_t* w = counts + ((size_t)t * G4R_COUNT_SUB + u) * G4R_COUNT_STRIDE;
-            sub_start[t * G4R_COUNT_SUB + u] = c;     // where this sub-counter's instances start inside the tile's range
-            c += *w;
-            *w = 0;                                   // the same word becomes the scatter cursor of (tile, sub)
-        }
+        const uint32_t c = counts[(size_t)t * G4R_COUNT_STRIDE];
+        counts[(size_t)t * G4R_COUNT_STRIDE] = 0;     // the same word becomes the scatter cursor of this tile
         ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
         run += c;
         const int b = ORDER_BUCKETS - 1 - min(ORDER_BUCKETS - 1, (int)((float)c * to_bucket));   // heaviest -> bucket 0
@@ -113,7 +104,7 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
     char* b = (char*)img;
     g4r_stage_begin(ST_TILE_SCAN, s);
     tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)(b + il.counts), (uint2*)(b + il.ranges), (uint32_t*)(b + il.header),
-                                                (uint32_t*)(b + il.order), (uint32_t*)(b + il.sub_start), il.tiles);
+                                                (uint32_t*)(b + il.order), il.tiles);
     g4r_stage_end(ST_TILE_SCAN, s);
     G4R_LAUNCH_OK("tile_scan_kernel");
     return G4R_OK;
@@ -124,7 +115,6 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
                                                             const uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
-                                                            const uint32_t* __restrict__ sub_start,
                                                             uint2* __restrict__ pairs, const uint32_t* __restrict__ header,
                                                             uint32_t capacity, uint32_t gx, uint32_t gy, TileOwner own) {
     if (header[0] > capacity) return;           // uniform: caller re-runs phase 2 with a larger buffer
@@ -151,8 +141,8 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
                 const uint32_t t = ty * gx + tx;
                 if (own.owns(t, gx)) {                                           // else: not this rank's tile
                     use[u] = true;
-                    mine[u] = atomicAdd(cursors + g4r_counter_word(t, (uint32_t)i), 1u);   // cursors start at 0
-                    first[u] = __ldg(&ranges[t].x) + __ldg(sub_start + t * G4R_COUNT_SUB + ((uint32_t)i & (G4R_COUNT_SUB - 1)));
+                    mine[u] = atomicAdd(cursors + (size_t)t * G4R_COUNT_STRIDE, 1u);       // cursors start at 0
+                    first[u] = __ldg(&ranges[t].x);
                 }
                 if (++tx == r.x1) { tx = r.x0; ++ty; }
             }
@@ -176,7 +166,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) count_tiles_kernel(int P, const int
     for (uint32_t ty = r.y0; ty < r.y1; ++ty)
         for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
             const uint32_t t = ty * gx + tx;
-            if (own.owns(t, gx)) atomicAdd(counts + g4r_counter_word(t, (uint32_t)i), 1u);
+            if (own.owns(t, gx)) atomicAdd(counts + (size_t)t * G4R_COUNT_STRIDE, 1u);
         }
 }
 
@@ -436,8 +426,7 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
     const float4* rec = (const float4*)((const char*)geom + gl.rec);
     g4r_stage_begin(ST_SCATTER, s);
     scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
-                                                                         (uint32_t*)(ib + il.counts), (const uint32_t*)(ib + il.sub_start),
-                                                                         (uint2*)(bb + bl.pairs),
+                                                                         (uint32_t*)(ib + il.counts), (uint2*)(bb + bl.pairs),
                                                                          (const uint32_t*)(ib + il.header), cap, (uint32_t)il.tiles_x,
                                                                          (uint32_t)il.tiles_y, g4r_owner(f));
     g4r_stage_end(ST_SCATTER, s);

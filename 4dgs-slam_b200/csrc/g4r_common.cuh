@@ -10,8 +10,7 @@
 #define G4R_HEADER_WORDS 8
 // Per-tile instance counters live one per 128-byte line: atomics on neighbouring words of one line serialise in a
 // single L2 slice (measured: 1.26 M atomics on 1200 packed counters = 95 us; one counter per line = ~10x faster).
-#define G4R_COUNT_STRIDE 32      // u32 words between two tile counters: one counter per 128-byte line
-#define G4R_COUNT_SUB 8          // sub-counters per tile; Gaussian i uses sub-counter i % 8 (see ImageLayout)
+#define G4R_COUNT_STRIDE 32
 
 // SH basis constants (values identical to DGR/cuda_rasterizer/auxiliary.h:22-39 and
 // gaussian_splatting/utils/sh_utils.py:24-41 -- they are the real SH normalisation constants).
@@ -45,7 +44,7 @@ struct GeomLayout {      // per-Gaussian state, saved for backward
     }
 };
 struct ImageLayout {     // per-pixel + per-tile state, saved for backward
-    size_t header, counts, ranges, final_T, n_contrib, order, sub_start, total;
+    size_t header, counts, ranges, final_T, n_contrib, order, total;
     int tiles_x, tiles_y, tiles;
     __host__ __device__ ImageLayout(int W, int H) {
         tiles_x = (W + G4R_TILE - 1) / G4R_TILE;
@@ -53,15 +52,11 @@ struct ImageLayout {     // per-pixel + per-tile state, saved for backward
         tiles = tiles_x * tiles_y;
         size_t o = 0;
         header = o;    o = g4r_align(o + G4R_HEADER_WORDS * 4);
-        // Histogram, then scatter cursors.  Atomics on ONE address are serialised by the L2 at ~30 ns each, and a tile receives
-        // ~1000 of them per frame, which bounded the projection and the scatter at ~32 us each; G4R_COUNT_SUB counters per tile,
-        // every one on its own 128-byte line, divide that chain.  Counter of (tile t, sub s): word (t*SUB + s) * STRIDE.
-        counts = o;    o = g4r_align(o + (size_t)tiles * G4R_COUNT_SUB * 4 * G4R_COUNT_STRIDE);
+        counts = o;    o = g4r_align(o + (size_t)tiles * 4 * G4R_COUNT_STRIDE);   // histogram, then scatter cursors
         ranges = o;    o = g4r_align(o + (size_t)tiles * 8);
         final_T = o;   o = g4r_align(o + (size_t)W * H * 4);
         n_contrib = o; o = g4r_align(o + (size_t)W * H * 4);
         order = o;     o = g4r_align(o + (size_t)tiles * 4);                       // tiles, heaviest first (launch order)
-        sub_start = o; o = g4r_align(o + (size_t)tiles * G4R_COUNT_SUB * 4);       // first slot of (tile, sub) inside the tile's range
         total = o + 256;
     }
 };
@@ -80,10 +75,6 @@ struct BinLayout {       // per-instance state; point_list is saved for backward
 //   [0]=dL/dmean2D.x [1]=dL/dmean2D.y [2]=dL/dconic.x [3]=dL/dconic.y [4]=dL/dconic.w
 //   [5]=dL/dopacity  [6]=dL/dcolor.r  [7]=dL/dcolor.g  [8]=dL/dcolor.b [9]=dL/ddepth
 #define G4R_ACC_STRIDE 12
-
-static __host__ __device__ __forceinline__ size_t g4r_counter_word(uint32_t tile, uint32_t gaussian) {
-    return ((size_t)tile * G4R_COUNT_SUB + (gaussian & (G4R_COUNT_SUB - 1))) * G4R_COUNT_STRIDE;
-}
 
 // ---- small device helpers ---------------------------------------------------------------
 // float -> int32 with the semantics of PTX cvt.rzi.s32.f32 (truncate, saturate, NaN -> 0),

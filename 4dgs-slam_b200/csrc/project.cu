@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     // ---- per-tile instance histogram (replaces tiles_touched + InclusiveSum) ----------------------------
     if (p.tile_counts == nullptr) return;           // sharded render: tiles are counted after the all-gather
     for (uint32_t ty_ = r.y0; ty_ < r.y1; ++ty_)
-        for (uint32_t tx_ = r.x0; tx_ < r.x1; ++tx_) atomicAdd(p.tile_counts + g4r_counter_word(ty_ * p.gx + tx_, (uint32_t)i), 1u);
+        for (uint32_t tx_ = r.x0; tx_ < r.x1; ++tx_) atomicAdd(p.tile_counts + (size_t)(ty_ * p.gx + tx_) * G4R_COUNT_STRIDE, 1u);
 }
 
 int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* img, int32_t* radii, int32_t* n_touched,

@@ -215,7 +215,7 @@ typedef struct G4RLayout {
     size_t img_final_T;     /* float[H*W]    */
     size_t img_n_contrib;   /* uint32[H*W]   */
     size_t img_ranges;      /* uint2[tiles]  */
-    size_t img_counts;      /* uint32[tiles*8*32]: 8 sub-counters per tile, one counter per 128-byte line */
+    size_t img_counts;      /* uint32[tiles*32]: one counter per 128-byte line */
     size_t img_header;      /* uint32[8]: [0] = N */
     size_t bin_point_list;  /* uint32[capacity] sorted Gaussian ids == reference point_list */
     size_t bin_pairs;       /* uint2[capacity]  unsorted (depth bits, id) */
