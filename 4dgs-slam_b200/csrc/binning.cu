@@ -126,31 +126,13 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
     const float4 b = ldg4(rec + (size_t)i * 3 + 1);
     const TileRect r = tile_rect(a.x, a.y, radius, gx, gy);
     const uint32_t key = __float_as_uint(b.z);  // depth bits, as duplicateWithKeys packs them (:104)
-    // The rectangle is walked four tiles at a time: the four cursor atomics (with return) are issued back to back and only
-    // then consumed, so a lane pays one L2 round trip per four tiles instead of one per tile (the kernel is bound by exactly
-    // that latency chain: the slowest lane of a warp used to serialise up to a dozen round trips).
-    const uint32_t w = r.x1 - r.x0, n = w * (r.y1 - r.y0);
-    uint32_t tx = r.x0, ty = r.y0;
-    for (uint32_t i0 = 0; i0 < n; i0 += 4) {
-        uint32_t first[4], mine[4];
-        bool use[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            use[u] = false;
-            if (i0 + u < n) {
-                const uint32_t t = ty * gx + tx;
-                if (own.owns(t, gx)) {                                           // else: not this rank's tile
-                    use[u] = true;
-                    mine[u] = atomicAdd(cursors + (size_t)t * G4R_COUNT_STRIDE, 1u);       // cursors start at 0
-                    first[u] = __ldg(&ranges[t].x);
-                }
-                if (++tx == r.x1) { tx = r.x0; ++ty; }
-            }
+    for (uint32_t ty = r.y0; ty < r.y1; ++ty)
+        for (uint32_t tx = r.x0; tx < r.x1; ++tx) {
+            const uint32_t t = ty * gx + tx;
+            if (!own.owns(t, gx)) continue;                                      // not this rank's tile
+            const uint32_t slot = __ldg(&ranges[t].x) + atomicAdd(cursors + (size_t)t * G4R_COUNT_STRIDE, 1u);   // cursors start at 0
+            pairs[slot] = make_uint2(key, (uint32_t)i);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (use[u]) pairs[first[u] + mine[u]] = make_uint2(key, (uint32_t)i);
-    }
 }
 
 // Sharded render: per-owned-tile histogram over the all-gathered records (project_kernel's fused histogram only sees
