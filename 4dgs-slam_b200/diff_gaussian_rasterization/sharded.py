@@ -33,7 +33,6 @@ and there is no fallback.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -77,3 +77,29 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dp, f)).read()
                 assert "g4r_oracle" not in text.replace("oracle/g4r_oracle.c follows", "") or f == "project.cu", (dp, f)
                 assert "import oracle" not in text and "from oracle" not in text
+
+
+def test_fused_rasterizer_surface_and_argument_checks():
+    """The opt-in raw-parameter module: exported, constructed like GaussianRasterizer, rejects CPU tensors
+    loudly (no CPU path) and malformed raw tensors with a message."""
+    import inspect
+
+    import pytest
+    import torch
+    import diff_gaussian_rasterization as dgr
+    assert "FusedGaussianRasterizer" in dgr.__all__ and "rasterize_gaussians_raw" in dgr.__all__
+    sig = inspect.signature(dgr.FusedGaussianRasterizer.forward)
+    assert list(sig.parameters)[1:] == ["xyz", "means2D", "features_dc", "features_rest", "opacity_raw", "scaling_raw", "rotation_raw",
+                                        "theta", "rho"]
+    rs = dgr.GaussianRasterizationSettings(image_height=8, image_width=8, tanfovx=1.0, tanfovy=1.0, bg=torch.ones(3), scale_modifier=1.0,
+                                           viewmatrix=torch.eye(4), projmatrix=torch.eye(4), projmatrix_raw=torch.eye(4), sh_degree=0,
+                                           campos=torch.zeros(3), prefiltered=False, debug=False)
+    P = 5
+    args = dict(xyz=torch.zeros(P, 3), means2D=torch.zeros(P, 3), features_dc=torch.zeros(P, 1, 3), features_rest=torch.zeros(P, 0, 3),
+                opacity_raw=torch.zeros(P, 1), scaling_raw=torch.zeros(P, 3), rotation_raw=torch.ones(P, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        dgr.FusedGaussianRasterizer(rs)(**args)
+    with pytest.raises(RuntimeError, match="scaling_raw"):
+        dgr.FusedGaussianRasterizer(rs)(**dict(args, scaling_raw=torch.zeros(P, 2)))
+    with pytest.raises(RuntimeError, match="features_dc"):
+        dgr.FusedGaussianRasterizer(rs)(**dict(args, features_dc=torch.zeros(P, 3)))

@@ -5,7 +5,6 @@
    no tan-fov clamping; SURVEY.md Appendix B items 3-5);
  * float32 and float64 builds agree; binning invariants; edge cases of the reference (nothing visible, ragged
    image sizes, precomputed colour / covariance inputs)."""
-import math
 
 import numpy as np
 import pytest
