@@ -487,7 +487,7 @@ def main():
             line["cuda_graph"] = {"value": 1000.0 / graph_ms, "unit": "frames/s", "ms_per_step": graph_ms, "capacity_overflow": graph_overflow,
                                   "note": "same step (fwd + loss + bwd through the public API) captured once with torch.cuda.graph and replayed; "
                                           "informational -- `value` above is the eager number"}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))
     if use_dist:
