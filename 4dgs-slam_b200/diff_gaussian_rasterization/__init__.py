@@ -395,12 +395,20 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                                      theta, rho, raster_settings)
 
 
+def _debug_sync(rs, t) -> None:
+    """`debug=True` (reference __init__.py:84-99,133-150): the reference synchronises after each call so that an asynchronous
+    kernel failure surfaces at the call that caused it (and dumps its arguments to snapshot_*.dump, which is not reproduced)."""
+    if getattr(rs, "debug", False) and t.is_cuda and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.synchronize(t.device)
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho,
                 raster_settings):
         color, radii, depth, opacity, n_touched, state = _forward_impl(
             means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+        _debug_sync(raster_settings, means3D)
         ctx.raster_settings = raster_settings
         ctx.num_rendered = state["N"]
         ctx.P = state["P"]
@@ -426,6 +434,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _dev_f32(rotations, device) if rotations.numel() else rotations,
             _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp,
             radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep)
+        _debug_sync(rs, means3D)
         grad_rho = tau[:3].view(1, -1)
         grad_theta = tau[3:6].view(1, -1)
         needs = ctx.needs_input_grad
