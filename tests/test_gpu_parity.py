@@ -61,6 +61,21 @@ def test_against_oracle(device, name):
     _assert_grads(rep, tol=2e-3)
 
 
+def test_config_c1_against_oracle(device):
+    """BASELINE.json config 0 (10 k Gaussians, 320x240, SH degree 0 -- the CPU-runnable case): forward AND backward of the
+    CUDA path against the CPU oracle, same bars as test_against_oracle."""
+    sc_cpu = config_scene("C1")
+    mine = runners.run_g4r(sc_cpu.to(device))
+    ora = runners.run_oracle(sc_cpu)
+    rep = runners.compare(mine, ora)
+    assert rep["num_rendered"][0] == rep["num_rendered"][1]
+    _assert_ints_exact(rep)
+    for k in ("color", "depth", "opacity"):
+        a, b = mine[k].cpu().numpy().reshape(-1), ora[k].reshape(-1)
+        assert (np.abs(a - b) > 1e-4 * max(1.0, float(np.abs(b).max()))).mean() < 2e-3, k
+    _assert_grads(rep, tol=2e-3)
+
+
 def _load_golden(path):
     z = np.load(path)
     W, H, deg, tfx, tfy, smod = z["in_scalars"]

@@ -176,3 +176,17 @@ def test_precomputed_paths_agree_with_scale_rotation_path(o64):
     fa, fb = o64.forward(scene_dict(a)), o64.forward(scene_dict(b))
     assert (fa["radii"] != fb["radii"]).sum() <= 1
     assert np.abs(fa["color"] - fb["color"]).max() < 1e-4        # cov3D_precomp is the float32 rounding of the same Sigma
+
+
+def test_config_c1_forward_on_cpu():
+    """BASELINE.json config 0: 10 k Gaussians, 320x240, SH degree 0, forward only on the CPU.  The float32 restatement and the
+    float64 one agree except where a threshold (alpha >= 1/255, T < 1e-4, tile rectangle rounding) flips."""
+    from tools.scenes import config_scene
+    sc = config_scene("C1")
+    f32 = Oracle("f32").forward(scene_dict(sc))
+    f64 = Oracle("f64").forward(scene_dict(sc))
+    assert f32["color"].shape == (3, 240, 320) and f32["radii"].shape == (10000,)
+    assert (f32["radii"] != f64["radii"]).mean() < 1e-3
+    assert abs(int(f32["num_rendered"]) - int(f64["num_rendered"])) <= 0.002 * int(f64["num_rendered"]) + 2
+    bad = np.abs(f32["color"] - f64["color"]) > 1e-4
+    assert bad.mean() < 5e-3, bad.mean()
