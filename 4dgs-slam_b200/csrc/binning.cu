@@ -115,8 +115,11 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
                                                             const uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
-                                                            uint2* __restrict__ pairs, const uint32_t* __restrict__ header,
+                                                            uint2* __restrict__ pairs, uint32_t* __restrict__ header,
                                                             uint32_t capacity, uint32_t gx, uint32_t gy, TileOwner own) {
+    // header[1] = capacity of this phase-2 run: the backward compares it with N (header[0]) so that a CUDA-graph replay
+    // whose instance count outgrew the captured capacity never walks an unwritten point_list.
+    if (blockIdx.x == 0 && threadIdx.x == 0) header[1] = capacity;
     if (header[0] > capacity) return;           // uniform: caller re-runs phase 2 with a larger buffer
     const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
     if (i >= P) return;
@@ -409,7 +412,7 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
     g4r_stage_begin(ST_SCATTER, s);
     scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
                                                                          (uint32_t*)(ib + il.counts), (uint2*)(bb + bl.pairs),
-                                                                         (const uint32_t*)(ib + il.header), cap, (uint32_t)il.tiles_x,
+                                                                         (uint32_t*)(ib + il.header), cap, (uint32_t)il.tiles_x,
                                                                          (uint32_t)il.tiles_y, g4r_owner(f));
     g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");

@@ -15,8 +15,11 @@ sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
 
 VARIANTS = {
     "default": {},
-    "no LPT (tiles in index order)": {"LPT": 0},
+    "round-1 backward kernel (BWD_LEGACY=1)": {"BWD_LEGACY": 1},
+    "forward one splat per trip (FWD_PAIR=0)": {"FWD_PAIR": 0},
 }
+if os.environ.get("G4R_VARIANTS"):          # e.g. G4R_VARIANTS='{"x": {"LPT": 0}}'
+    VARIANTS = {"default": {}, **json.loads(os.environ["G4R_VARIANTS"])}
 # Round-1 history (profiles/r01_v7_tune_matrix.json) also covered shapes that were measured and dropped from the source:
 # forward capped at 56 / 48 registers (9 / 10 CTAs per SM), backward CTA per tile with 64 / 128 staged splats, backward CTA
 # per half tile with 128 staged.
@@ -57,10 +60,19 @@ def worker():
         row = {}
         for k in ("color", "depth", "opacity", "radii", "n_touched"):
             row["sha_" + k] = hashlib.sha1(r[k].detach().cpu().numpy().tobytes()).hexdigest()[:16]
+        gpath = f"/tmp/g4r_tune_grads_{name}.pt"
+        base_g = torch.load(gpath) if os.path.exists(gpath) else None
+        save_g = {}
         for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dopacity", "dL_dshs", "dL_dscales", "dL_drots", "dL_dtau"):
             if r.get(k) is not None:
                 g = r[k].detach().double()
                 row["g_" + k] = [float(g.norm()), float(g.sum())]
+                save_g[k] = g.cpu()
+                if base_g is not None:       # relative L2 distance to the first (default) variant's gradient
+                    b = base_g[k].to(g.device)
+                    row["gl2_" + k] = float((g - b).norm() / (b.norm() + 1e-30))
+        if base_g is None:
+            torch.save(save_g, gpath)
         lib.g4r_profile_enable(1)
         row["eager_ms"] = timeit(lambda: runners.run_public_api(sc, dgr), warmup=3, iters=20)
         n_st = lib.g4r_profile_stage_count()
@@ -79,8 +91,10 @@ def worker():
 
 def main():
     import torch
-    if os.path.exists(SCENE_FILE):
-        os.remove(SCENE_FILE)
+    import glob
+    for f in [SCENE_FILE] + glob.glob("/tmp/g4r_tune_grads_*.pt"):
+        if os.path.exists(f):
+            os.remove(f)
     torch.save(scenes(), SCENE_FILE)
     results = {}
     for vname, env_add in VARIANTS.items():
@@ -113,6 +127,9 @@ def main():
                     gerr = max(gerr, abs(row[k][0] - b[k][0]) / (abs(b[k][0]) + 1e-30))
             row["outputs_identical_to_default"] = same
             row["grad_norm_rel_diff"] = gerr
+            gl2 = max([row[k] for k in row if k.startswith("gl2_")] + [0.0])
+            row["grad_l2_rel_to_default_max"] = gl2
+            gerr = max(gerr, gl2)
             st = row["stage_us"]
             print(f"{vname:38s} {sname:14s} eager {row['eager_ms']:.3f} graph {row['graph_ms'] if isinstance(row['graph_ms'], str) else round(row['graph_ms'], 3)}"
                   f" | fwd {st.get('composite_forward')} bwd {st.get('composite_backward')} sort {st.get('tile_sort')} scan {st.get('tile_scan')}"
