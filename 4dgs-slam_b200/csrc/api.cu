@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <new>
@@ -19,37 +20,44 @@ int g4r_set_error(int code, const char* fmt, ...) {
     return code;
 }
 
-// ---- per-stage profiling: process-wide, off by default (single-stream use only) ---------------------------------------------------
+// ---- per-stage profiling: process-wide, off by default -----------------------------------------------------------------------------
+// Autograd runs the backward on its own thread(s), so stage_begin / stage_end / read can race: the flag is an atomic (the
+// fast path when profiling is off) and everything else is serialised by one mutex.
 struct StageProfile {
-    bool enabled = false;
+    std::atomic<bool> enabled{false};
     bool created = false;
     cudaEvent_t ev[ST_COUNT][2];
     bool pending[ST_COUNT] = {};
     double ms[ST_COUNT] = {};
     int64_t count[ST_COUNT] = {};
+    std::mutex mu;
 };
-static StageProfile g_prof;   // process-wide: autograd runs backward on its own thread
+static StageProfile g_prof;
 static const char* const k_stage_names[ST_COUNT] = {"project", "tile_scan", "scatter", "tile_sort", "composite_forward",
                                                     "composite_backward", "gaussian_backward"};
 
-static void prof_collect() {
+static void prof_collect_locked(int only_stage = -1) {
     for (int i = 0; i < ST_COUNT; ++i)
-        if (g_prof.pending[i]) {
+        if (g_prof.pending[i] && (only_stage < 0 || i == only_stage)) {
+            // a stage whose end event has not fired yet stays pending (it is folded in by a later read)
+            if (cudaEventQuery(g_prof.ev[i][1]) != cudaSuccess) { cudaGetLastError(); continue; }
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]) == cudaSuccess) { g_prof.ms[i] += ms; g_prof.count[i]++; }
             g_prof.pending[i] = false;
         }
 }
 void g4r_stage_begin(int stage, cudaStream_t s) {
-    if (!g_prof.enabled) return;
+    if (!g_prof.enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     if (g_prof.pending[stage]) {            // the previous launch of this stage was not collected: fold it in now
         cudaEventSynchronize(g_prof.ev[stage][1]);
-        prof_collect();
+        prof_collect_locked(stage);
     }
     cudaEventRecord(g_prof.ev[stage][0], s);
 }
 void g4r_stage_end(int stage, cudaStream_t s) {
-    if (!g_prof.enabled) return;
+    if (!g_prof.enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     cudaEventRecord(g_prof.ev[stage][1], s);
     g_prof.pending[stage] = true;
 }
@@ -112,7 +120,7 @@ static int check_gaussians(const G4RFrame* f, const G4RGaussians* g) {
 extern "C" {
 
 const char* g4r_last_error(void) { return g_err; }
-int g4r_version(void) { return 4; }
+int g4r_version(void) { return 5; }
 void g4r_struct_sizes(int32_t* out5) {
     out5[0] = (int32_t)sizeof(G4RFrame); out5[1] = (int32_t)sizeof(G4RGaussians); out5[2] = (int32_t)sizeof(G4RForwardOut);
     out5[3] = (int32_t)sizeof(G4RBackwardIO); out5[4] = (int32_t)sizeof(G4RLayout);
@@ -145,6 +153,7 @@ void g4r_context_destroy(G4RContext* c) {
 size_t g4r_geom_bytes(int32_t P) { return GeomLayout(P < 0 ? 0 : P).total; }
 size_t g4r_image_bytes(int32_t W, int32_t H) { return ImageLayout(W < 1 ? 1 : W, H < 1 ? 1 : H).total; }
 size_t g4r_binning_bytes(int64_t capacity) { return BinLayout(capacity).total; }
+size_t g4r_sort_scratch_bytes(int64_t capacity) { return SortLayout(capacity).total; }
 size_t g4r_backward_scratch_bytes(int32_t P) { return g4r_align((size_t)(P < 1 ? 1 : P) * G4R_ACC_STRIDE * sizeof(float)) + 256; }
 
 int g4r_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, G4RLayout* out) {
@@ -155,7 +164,7 @@ int g4r_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, G4RLayout* out
     out->geom_rec = gl.rec; out->geom_clamped = gl.clamped;
     out->img_final_T = il.final_T; out->img_n_contrib = il.n_contrib; out->img_ranges = il.ranges;
     out->img_counts = il.counts; out->img_header = il.header;
-    out->bin_point_list = bl.point_list; out->bin_pairs = bl.pairs;
+    out->bin_point_list = bl.point_list; out->bin_pairs = SortLayout(capacity).pairs;
     return G4R_OK;
 }
 
@@ -196,15 +205,16 @@ int64_t g4r_wait_num_rendered(G4RContext* ctx) {
 }
 
 int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g, void* geom, void* img, void* binning,
-                       int64_t capacity, const G4RForwardOut* out, void* stream) {
+                       void* sort_scratch, int64_t capacity, const G4RForwardOut* out, void* stream) {
     int rc;
     if ((rc = check_frame(f, false)) != G4R_OK) return rc;
     if (!g || g->P < 0) return g4r_set_error(G4R_EINVAL, "gaussians is NULL or P is negative");   // phase 2 only needs P
     if (!out || !out->color || !out->depth || !out->opacity) return g4r_set_error(G4R_EINVAL, "output images are NULL");
-    if (!img || !binning) return g4r_set_error(G4R_EINVAL, "img/binning buffers are NULL");
+    if (!img || !binning || !sort_scratch) return g4r_set_error(G4R_EINVAL, "img/binning/sort_scratch buffers are NULL");
     if (g->P > 0 && (!geom || !out->radii || !out->n_touched)) return g4r_set_error(G4R_EINVAL, "geom/radii/n_touched are NULL");
     if (capacity < 0) return g4r_set_error(G4R_EINVAL, "capacity is negative");
-    if (((uintptr_t)geom | (uintptr_t)img | (uintptr_t)binning) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
+    if (((uintptr_t)geom | (uintptr_t)img | (uintptr_t)binning | (uintptr_t)sort_scratch) & 15u)
+        return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     if (g->P > 0) {
         if (ctx && ctx->renders_since_project > 0) {
@@ -215,7 +225,7 @@ int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g
             G4R_CUDA_OK(cudaMemsetAsync(out->n_touched, 0, sizeof(int32_t) * (size_t)g->P, s));
         }
         if (ctx) ctx->renders_since_project++;
-        if ((rc = launch_scatter_sort(*f, g->P, out->radii, geom, img, binning, capacity, s)) != G4R_OK) return rc;
+        if ((rc = launch_scatter_sort(*f, g->P, out->radii, geom, img, binning, sort_scratch, capacity, ctx == nullptr, s)) != G4R_OK) return rc;
     }
     return launch_composite_forward(*f, g->P, geom, img, binning, capacity, *out, s);
 }
@@ -244,10 +254,8 @@ int g4r_backward_gaussians(const G4RFrame* f, const G4RGaussians* g, const int32
     cudaStream_t s = (cudaStream_t)stream;
     G4R_CUDA_OK(cudaMemsetAsync(io->dL_dtau, 0, sizeof(float) * 8, s));
     if (g->P == 0) return G4R_OK;
-    if (!io->dL_dmeans3D || !io->dL_dmeans2D || !io->dL_dopacity) return g4r_set_error(G4R_EINVAL, "dL_dmeans3D/dL_dmeans2D/dL_dopacity are NULL");
-    if (g->shs && !io->dL_dshs) return g4r_set_error(G4R_EINVAL, "dL_dshs is NULL although shs was given");
-    if (g->activation == G4R_ACT_RAW && f->sh_coeffs > 1 && !io->dL_dshs_rest) return g4r_set_error(G4R_EINVAL, "dL_dshs_rest is NULL in raw-parameter mode");
-    if (g->activation == G4R_ACT_RAW && (!io->dL_dscales || !io->dL_drotations)) return g4r_set_error(G4R_EINVAL, "raw-parameter mode writes dL_dscales and dL_drotations");
+    // Every per-Gaussian output is optional: a NULL pointer means the caller does not need that gradient (autograd's
+    // needs_input_grad; e.g. pose tracking consumes dL_dtau only) and the kernel skips those stores.
     if (!radii || !geom || !acc) return g4r_set_error(G4R_EINVAL, "saved state / accumulators are NULL");
     if (((uintptr_t)geom | (uintptr_t)acc) & 15u) return g4r_set_error(G4R_EINVAL, "scratch buffers must be 16-byte aligned");
     if (io->dL_drotations && ((uintptr_t)io->dL_drotations & 15u)) return g4r_set_error(G4R_EINVAL, "dL_drotations must be 16-byte aligned");
@@ -306,20 +314,28 @@ int g4r_count_tiles(G4RContext* ctx, const G4RFrame* f, int32_t P_all, const int
     return G4R_OK;
 }
 
+int64_t g4r_overflow_status(int reset) {
+    unsigned int v = 0;
+    const int rc = g4r_overflow_read(reset, &v);
+    return rc != G4R_OK ? (int64_t)rc : (int64_t)v;
+}
+
 int g4r_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
     if (on && !g_prof.created) {
         for (int i = 0; i < ST_COUNT; ++i)
             for (int j = 0; j < 2; ++j) G4R_CUDA_OK(cudaEventCreate(&g_prof.ev[i][j]));
         g_prof.created = true;
     }
-    g_prof.enabled = on != 0;
+    g_prof.enabled.store(on != 0);
     return G4R_OK;
 }
 int g4r_profile_stage_count(void) { return ST_COUNT; }
 const char* g4r_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? k_stage_names[i] : ""; }
 int g4r_profile_read(double* ms_out, int64_t* count_out, int reset) {
     // caller must have synchronised the stream(s) the stages ran on
-    prof_collect();
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    prof_collect_locked();
     for (int i = 0; i < ST_COUNT; ++i) {
         if (ms_out) ms_out[i] = g_prof.ms[i];
         if (count_out) count_out[i] = g_prof.count[i];

@@ -113,14 +113,32 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 // 3. scatter (depth bits, id) into tile segments
 // ---------------------------------------------------------------------------------------------
+// Largest N that did not fit its capacity in a forward that ran without host read-back (ctx == NULL: CUDA-graph capture
+// and replay).  One word per device (a __device__ variable exists once per device); read and cleared by
+// g4r_overflow_status().  Eager forwards re-run phase 2 on overflow and do not touch it.
+__device__ unsigned int g_overflow_max = 0;
+
+int g4r_overflow_read(int reset, unsigned int* out) {
+    G4R_CUDA_OK(cudaDeviceSynchronize());
+    G4R_CUDA_OK(cudaMemcpyFromSymbol(out, g_overflow_max, sizeof(unsigned int)));
+    if (reset && *out) {
+        const unsigned int zero = 0;
+        G4R_CUDA_OK(cudaMemcpyToSymbol(g_overflow_max, &zero, sizeof(unsigned int)));
+    }
+    return G4R_OK;
+}
+
 __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,
                                                             const uint2* __restrict__ ranges, uint32_t* __restrict__ cursors,
                                                             uint2* __restrict__ pairs, uint32_t* __restrict__ header,
-                                                            uint32_t capacity, uint32_t gx, uint32_t gy, TileOwner own) {
+                                                            uint32_t capacity, uint32_t gx, uint32_t gy, TileOwner own, bool record_overflow) {
     // header[1] = capacity of this phase-2 run: the backward compares it with N (header[0]) so that a CUDA-graph replay
     // whose instance count outgrew the captured capacity never walks an unwritten point_list.
     if (blockIdx.x == 0 && threadIdx.x == 0) header[1] = capacity;
-    if (header[0] > capacity) return;           // uniform: caller re-runs phase 2 with a larger buffer
+    if (header[0] > capacity) {                 // uniform: an eager caller re-runs phase 2 with a larger buffer
+        if (record_overflow && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&g_overflow_max, header[0]);
+        return;
+    }
     const int i = blockIdx.x * G4R_BLOCK + threadIdx.x;
     if (i >= P) return;
     const int radius = radii[i];
@@ -401,24 +419,26 @@ __global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __res
 }
 
 int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
-                        int64_t capacity, cudaStream_t s) {
+                        void* sort_scratch, int64_t capacity, bool record_overflow, cudaStream_t s) {
     const GeomLayout gl(P);
     const ImageLayout il(f.width, f.height);
     const BinLayout bl(capacity);
+    const SortLayout sl(capacity);
     char* ib = (char*)img;
     char* bb = (char*)binning;
+    char* sb = (char*)sort_scratch;
     const uint32_t cap = (uint32_t)(capacity > 0xffffffffll ? 0xffffffffll : capacity);
     const float4* rec = (const float4*)((const char*)geom + gl.rec);
     g4r_stage_begin(ST_SCATTER, s);
     scatter_kernel<<<(P + G4R_BLOCK - 1) / G4R_BLOCK, G4R_BLOCK, 0, s>>>(P, radii, rec, (const uint2*)(ib + il.ranges),
-                                                                         (uint32_t*)(ib + il.counts), (uint2*)(bb + bl.pairs),
+                                                                         (uint32_t*)(ib + il.counts), (uint2*)(sb + sl.pairs),
                                                                          (uint32_t*)(ib + il.header), cap, (uint32_t)il.tiles_x,
-                                                                         (uint32_t)il.tiles_y, g4r_owner(f));
+                                                                         (uint32_t)il.tiles_y, g4r_owner(f), record_overflow);
     g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");
     static const bool lpt = g4r_tunable("LPT", 1) != 0;
     g4r_stage_begin(ST_TILE_SORT, s);
-    tile_sort_kernel<<<il.tiles, G4R_BLOCK, 0, s>>>((const uint2*)(ib + il.ranges), (uint2*)(bb + bl.pairs), (uint2*)(bb + bl.pairs_alt),
+    tile_sort_kernel<<<il.tiles, G4R_BLOCK, 0, s>>>((const uint2*)(ib + il.ranges), (uint2*)(sb + sl.pairs), (uint2*)(sb + sl.pairs_alt),
                                                     (uint32_t*)(bb + bl.point_list), (const uint32_t*)(ib + il.header), cap,
                                                     lpt ? (const uint32_t*)(ib + il.order) : nullptr);
     g4r_stage_end(ST_TILE_SORT, s);

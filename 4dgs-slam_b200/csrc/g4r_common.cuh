@@ -60,14 +60,22 @@ struct ImageLayout {     // per-pixel + per-tile state, saved for backward
         total = o + 256;
     }
 };
-struct BinLayout {       // per-instance state; point_list is saved for backward
-    size_t point_list, pairs, pairs_alt, total;
+struct BinLayout {       // per-instance state SAVED for backward (the reference's binningBuffer): the sorted id list
+    size_t point_list, total;
     __host__ __device__ explicit BinLayout(int64_t cap) {
         size_t c = (size_t)(cap < 1 ? 1 : cap);
         size_t o = 0;
         point_list = o; o = g4r_align(o + c * 4);
+        total = o + 256;
+    }
+};
+struct SortLayout {      // per-instance scratch of the forward only (dies with the call): unsorted (depth bits, id) pairs
+    size_t pairs, pairs_alt, total;
+    __host__ __device__ explicit SortLayout(int64_t cap) {
+        size_t c = (size_t)(cap < 1 ? 1 : cap);
+        size_t o = 0;
         pairs = o;      o = g4r_align(o + c * 8);
-        pairs_alt = o;  o = g4r_align(o + c * 8);
+        pairs_alt = o;  o = g4r_align(o + c * 8);      // ping-pong buffer of the oversized-tile radix sort
         total = o + 256;
     }
 };
@@ -159,7 +167,8 @@ int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s);
 int launch_count_tiles(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, cudaStream_t s);
 int launch_tile_rows(const G4RFrame& f, int P, const int32_t* radii, const void* geom, int32_t* rows, cudaStream_t s);
 int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
-                        int64_t capacity, cudaStream_t s);
+                        void* sort_scratch, int64_t capacity, bool record_overflow, cudaStream_t s);
+int g4r_overflow_read(int reset, unsigned int* out);
 int launch_composite_forward(const G4RFrame& f, int P, const void* geom, void* img, const void* binning, int64_t capacity,
                              const G4RForwardOut& out, cudaStream_t s);
 int launch_composite_backward(const G4RFrame& f, int P, const void* geom, const void* img, const void* binning,

@@ -55,11 +55,11 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
     if (in_range && !visible) {
         // invisible Gaussian: all gradients are zero
         const size_t o3 = (size_t)i * 3;
-        p.dL_dmeans3D[o3] = 0.f; p.dL_dmeans3D[o3 + 1] = 0.f; p.dL_dmeans3D[o3 + 2] = 0.f;
-        p.dL_dmeans2D[o3] = 0.f; p.dL_dmeans2D[o3 + 1] = 0.f; p.dL_dmeans2D[o3 + 2] = 0.f;
-        p.dL_dopacity[i] = 0.f;
+        if (p.dL_dmeans3D) { p.dL_dmeans3D[o3] = 0.f; p.dL_dmeans3D[o3 + 1] = 0.f; p.dL_dmeans3D[o3 + 2] = 0.f; }
+        if (p.dL_dmeans2D) { p.dL_dmeans2D[o3] = 0.f; p.dL_dmeans2D[o3 + 1] = 0.f; p.dL_dmeans2D[o3 + 2] = 0.f; }
+        if (p.dL_dopacity) p.dL_dopacity[i] = 0.f;
         if (kRaw) {
-            float* d = p.dL_dshs + o3; d[0] = 0.f; d[1] = 0.f; d[2] = 0.f;
+            if (p.dL_dshs) { float* d = p.dL_dshs + o3; d[0] = 0.f; d[1] = 0.f; d[2] = 0.f; }
             if (p.dL_dshs_rest) { float* r = p.dL_dshs_rest + (size_t)i * (p.M - 1) * 3; for (int k = 0; k < (p.M - 1) * 3; ++k) r[k] = 0.f; }
         } else if (p.dL_dshs) { float* d = p.dL_dshs + (size_t)i * p.M * 3; for (int k = 0; k < p.M * 3; ++k) d[k] = 0.f; }
         if (p.dL_dcolors_precomp) { p.dL_dcolors_precomp[o3] = 0.f; p.dL_dcolors_precomp[o3 + 1] = 0.f; p.dL_dcolors_precomp[o3 + 2] = 0.f; }
@@ -230,10 +230,11 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
             const bool split = kRaw && p.M > 1;
             const float* sh = kRaw ? p.shs + (size_t)i * 3 : p.shs + (size_t)i * p.M * 3;
             const float* shr = split ? p.shs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : sh;
+            const bool want_dsh = p.dL_dshs != nullptr;      // NULL: the caller does not need dL/dSH (needs_input_grad)
             float* dsh = kRaw ? p.dL_dshs + (size_t)i * 3 : p.dL_dshs + (size_t)i * p.M * 3;
             float* dshr = split ? p.dL_dshs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : dsh;
 #define SHV(k) v3(__ldg(((k) == 0 ? sh : shr) + (k) * 3), __ldg(((k) == 0 ? sh : shr) + (k) * 3 + 1), __ldg(((k) == 0 ? sh : shr) + (k) * 3 + 2))
-#define DSH(k, f) { const float f__ = (f); float* d__ = ((k) == 0 ? dsh : dshr) + (k) * 3; d__[0] = f__ * dRGB.x; d__[1] = f__ * dRGB.y; d__[2] = f__ * dRGB.z; }
+#define DSH(k, f) { if (want_dsh) { const float f__ = (f); float* d__ = ((k) == 0 ? dsh : dshr) + (k) * 3; d__[0] = f__ * dRGB.x; d__[1] = f__ * dRGB.y; d__[2] = f__ * dRGB.z; } }
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;    // dL/d(dir) accumulated as dot(dRGB/d(dir), dRGB)
             DSH(0, G4R_SH_C0);
             if (p.D > 0) {
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
                     }
                 }
             }
-            for (int k = K * 3; k < p.M * 3; ++k) dshr[k] = 0.f;    // inactive coefficients (reference: torch::zeros); K >= 1
+            if (want_dsh) for (int k = K * 3; k < p.M * 3; ++k) dshr[k] = 0.f;    // inactive coefficients (reference: torch::zeros); K >= 1
 #undef SHV
 #undef DSH
             // d normalize(v)/dv applied to dL/d(dir) (auxiliary.h:109-120)
@@ -333,13 +334,15 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
         }
 
         const size_t o3 = (size_t)i * 3;
-        p.dL_dmeans3D[o3] = dmean.x; p.dL_dmeans3D[o3 + 1] = dmean.y; p.dL_dmeans3D[o3 + 2] = dmean.z;
-        p.dL_dmeans2D[o3] = dmean2D_x; p.dL_dmeans2D[o3 + 1] = dmean2D_y; p.dL_dmeans2D[o3 + 2] = 0.f;
-        if (kRaw) {                                                          // d sigmoid(x) = o (1 - o) dx; o as the forward stored it
-            const float o = __ldg(reinterpret_cast<const float*>(p.rec + (size_t)i * 3 + 1) + 1);
-            p.dL_dopacity[i] = dopacity * o * (1.0f - o);
-        } else {
-            p.dL_dopacity[i] = dopacity;
+        if (p.dL_dmeans3D) { p.dL_dmeans3D[o3] = dmean.x; p.dL_dmeans3D[o3 + 1] = dmean.y; p.dL_dmeans3D[o3 + 2] = dmean.z; }
+        if (p.dL_dmeans2D) { p.dL_dmeans2D[o3] = dmean2D_x; p.dL_dmeans2D[o3 + 1] = dmean2D_y; p.dL_dmeans2D[o3 + 2] = 0.f; }
+        if (p.dL_dopacity) {
+            if (kRaw) {                                                      // d sigmoid(x) = o (1 - o) dx; o as the forward stored it
+                const float o = __ldg(reinterpret_cast<const float*>(p.rec + (size_t)i * 3 + 1) + 1);
+                p.dL_dopacity[i] = dopacity * o * (1.0f - o);
+            } else {
+                p.dL_dopacity[i] = dopacity;
+            }
         }
     }
 

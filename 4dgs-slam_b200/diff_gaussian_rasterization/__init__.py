@@ -112,12 +112,14 @@ def _load_library() -> ctypes.CDLL:
     lib.g4r_image_bytes.argtypes = [i32, i32]
     lib.g4r_binning_bytes.restype = sz
     lib.g4r_binning_bytes.argtypes = [i64]
+    lib.g4r_sort_scratch_bytes.restype = sz
+    lib.g4r_sort_scratch_bytes.argtypes = [i64]
     lib.g4r_backward_scratch_bytes.restype = sz
     lib.g4r_backward_scratch_bytes.argtypes = [i32]
     lib.g4r_forward_project.restype = ctypes.c_int
     lib.g4r_forward_project.argtypes = [vp, ctypes.POINTER(_Frame), ctypes.POINTER(_Gaussians), vp, vp, vp, vp, vp]
     lib.g4r_forward_render.restype = ctypes.c_int
-    lib.g4r_forward_render.argtypes = [vp, ctypes.POINTER(_Frame), ctypes.POINTER(_Gaussians), vp, vp, vp, i64,
+    lib.g4r_forward_render.argtypes = [vp, ctypes.POINTER(_Frame), ctypes.POINTER(_Gaussians), vp, vp, vp, vp, i64,
                                        ctypes.POINTER(_ForwardOut), vp]
     lib.g4r_wait_num_rendered.restype = i64
     lib.g4r_wait_num_rendered.argtypes = [vp]
@@ -126,6 +128,8 @@ def _load_library() -> ctypes.CDLL:
                                  ctypes.POINTER(_BackwardIO), vp]
     lib.g4r_mark_visible.restype = ctypes.c_int
     lib.g4r_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.g4r_overflow_status.restype = i64
+    lib.g4r_overflow_status.argtypes = [ctypes.c_int]
     lib.g4r_layout.restype = ctypes.c_int
     lib.g4r_layout.argtypes = [i32, i32, i32, i64, ctypes.POINTER(_Layout)]
     # the ctypes mirrors above must have exactly the C layout of include/g4r.h
@@ -135,8 +139,8 @@ def _load_library() -> ctypes.CDLL:
     if list(sizes) != mine:
         raise ImportError(f"diff_gaussian_rasterization: struct layout mismatch between libg4r.so {list(sizes)} and the Python "
                           f"bindings {mine}; rebuild the library")
-    if lib.g4r_version() != 4:
-        raise ImportError(f"diff_gaussian_rasterization: libg4r.so has ABI version {lib.g4r_version()}, expected 4; rebuild it")
+    if lib.g4r_version() != 5:
+        raise ImportError(f"diff_gaussian_rasterization: libg4r.so has ABI version {lib.g4r_version()}, expected 5; rebuild it")
     return lib
 
 
@@ -166,27 +170,36 @@ def _context(device: torch.device) -> int:
     return h
 
 
-# instance-capacity hint per device: high-water mark of num_rendered with slow decay
+# instance-capacity hint per (device, W, H): high-water mark of num_rendered with slow decay.  The autograd engine runs
+# backward on its own threads and applications may render from several threads, hence the lock.
+_state_lock = threading.Lock()
 _cap_hint: dict = {}
 
-# CUDA-graph capture: capacity = hint x this factor; (image state, capacity, header offset) of every captured forward
+# CUDA-graph capture: no host read-back is possible, so phase 2 gets capacity = hint x this factor.
 _GRAPH_CAPACITY_FACTOR = 2.0
-_captured: list = []
 
 
-def captured_overflow() -> bool:
-    """True if, in the most recent replay, any forward captured in a CUDA graph produced more (tile, Gaussian) instances
-    than the capacity fixed at capture time (its outputs are then stale).  Synchronises the device; call it as often
-    as the application needs the guarantee, then re-capture after more eager warm-up iterations."""
+def captured_overflow(device=None) -> bool:
+    """True if, since the last call, a forward that ran WITHOUT host read-back (i.e. captured in a CUDA graph and replayed)
+    produced more (tile, Gaussian) instances than the capacity fixed at capture time.  Such a replay leaves the forward
+    outputs stale and its backward returns zero gradients (the kernels compare N with the capacity on the device and
+    exit untouched).  The flag lives in the library (one word per device, set by the kernel that detects the overflow), so
+    it does not depend on which graphs are still alive.  Synchronises the device and clears the flag; after a True, run a
+    few eager iterations (they update the capacity hint) and capture again."""
+    devs = [torch.device(device).index] if device is not None else list(range(torch.cuda.device_count()))
     bad = False
-    for img, cap, off in _captured:
-        n = int(img[off:off + 4].view(torch.int32).item()) & 0xffffffff
-        bad = bad or n > cap
+    for d in devs:
+        with torch.cuda.device(d if d is not None else torch.cuda.current_device()):
+            n = int(_lib.g4r_overflow_status(1))
+            if n < 0:
+                _check(n)
+            bad = bad or n > 0
     return bad
 
 
 def reset_captured() -> None:
-    _captured.clear()
+    """Clears the overflow flag on every device (kept for API compatibility with round 1)."""
+    captured_overflow()
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -296,18 +309,20 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw)
         out = _ForwardOut(color.data_ptr(), depth.data_ptr(), opacity.data_ptr(), radii.data_ptr(), n_touched.data_ptr())
 
+        key = (device.index, W, H)
+        with _state_lock:
+            hint = _cap_hint.get(key, 0)
         if torch.cuda.is_current_stream_capturing():
             # CUDA-graph capture (torch.cuda.graph around forward + loss + backward): no host read-back is possible, so
-            # phase 2 gets a generous fixed capacity derived from the eager warm-up iterations.  Replays whose instance
-            # count outgrows it leave the outputs untouched; `captured_overflow()` reports that after a replay.
-            key = (device.index, W, H)
-            cap = int(max(_cap_hint.get(key, 0), 4 * P) * _GRAPH_CAPACITY_FACTOR) + 4096
+            # phase 2 gets a generous fixed capacity derived from the eager warm-up iterations.  A replay whose instance
+            # count outgrows it leaves the outputs untouched, its backward returns zeros, and `captured_overflow()` reports it.
+            cap = int(max(hint, 4 * P) * _GRAPH_CAPACITY_FACTOR) + 4096
             binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
+            sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), **u8)
             _check(_lib.g4r_forward_project(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                             radii.data_ptr(), n_touched.data_ptr(), stream))
             _check(_lib.g4r_forward_render(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
-                                           binning.data_ptr(), cap, ctypes.byref(out), stream))
-            _captured.append((img, cap, _layout(P, W, H, cap).img_header))
+                                           binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
             if raw is not None and raw[0] is not None:
                 keep.append(raw[0])
             state = dict(P=P, N=-1, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
@@ -317,49 +332,54 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
                                         radii.data_ptr(), n_touched.data_ptr(), stream))
         # Phase 2 is enqueued with a speculative capacity; N is checked only after everything is in the
         # stream, so the device never waits for the host (the reference blocks on a cudaMemcpy instead,
-        # rasterizer_impl.cu:284).
-        key = (device.index, W, H)
-        hint = _cap_hint.get(key, 0)
+        # rasterizer_impl.cu:284).  `binning` (the sorted id list) is saved for backward; `sort_scratch` (the unsorted
+        # pairs, 4x larger) dies with this call -- the caching allocator recycles it stream-ordered.
         cap = int(max(hint, 4 * P) * 1.25) + 4096 if hint == 0 else int(hint * 1.25) + 4096
         binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
+        sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), **u8)
         _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
-                                       binning.data_ptr(), cap, ctypes.byref(out), stream))
+                                       binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
         N = int(_lib.g4r_wait_num_rendered(ctx))
         if N < 0:
             _check(N)
         if N > cap:
             cap = N
             binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
+            sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), **u8)
             _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
-                                           binning.data_ptr(), cap, ctypes.byref(out), stream))
-        _cap_hint[key] = max(N, int(hint * 0.95))
+                                           binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
+        with _state_lock:
+            _cap_hint[key] = max(N, int(_cap_hint.get(key, 0) * 0.95))
     if raw is not None and raw[0] is not None:
         keep.append(raw[0])
-    state = dict(P=P, N=N, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
+    state = dict(P=P, N=N, geom=geom, img=img, binning=binning, sort_scratch=sort_scratch, capacity=cap, frame=(frame, keep))
     return color, radii, depth, opacity, n_touched, state
 
 
 def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii, geom, img, binning,
-                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None, raw=None):
-    """`raw` = None or (features_rest | None, scale_dim, raw opacities): gradients are then w.r.t. the raw parameters and a
-    tenth element, the gradient of features_rest, is appended to the returned tuple."""
+                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None, raw=None, want=None):
+    """`raw` = None or (features_rest | None, scale_dim): gradients are then w.r.t. the raw parameters and a tenth element, the
+    gradient of features_rest, is appended to the returned tuple.  `want` = dict of booleans (means3D, means2D, sh,
+    colors, opacities, scales, rotations, cov) from autograd's needs_input_grad: gradients nobody asked for are neither
+    allocated nor written (pose tracking only consumes dL/dtau, utils/slam_frontend.py:441-448); missing keys mean True."""
     device = means3D.device
-    H, W = int(rs.image_height), int(rs.image_width)
     f32 = dict(dtype=torch.float32, device=device)
+    w = (lambda k: True) if want is None else (lambda k: bool(want.get(k, True)))
     M = int(sh.size(1)) if sh.numel() else 0
     grad_rest = None
     if raw is not None and raw[0] is not None:
         M = 1 + int(raw[0].size(1))
-        grad_rest = torch.empty((P, M - 1, 3), **f32)
+        if w("sh"):
+            grad_rest = torch.empty((P, M - 1, 3), **f32)
     tau = torch.empty((8,), **f32)
-    grad_means3D = torch.empty((P, 3), **f32)
-    grad_means2D = torch.empty((P, 3), **f32)
-    grad_opacities = torch.empty(opacities_shape, **f32)
-    grad_sh = torch.empty((P, 1 if raw is not None else M, 3), **f32) if sh.numel() else None
-    grad_colors = torch.empty((P, 3), **f32) if colors_precomp.numel() else None
-    grad_scales = torch.empty((P, raw[1] if raw is not None else 3), **f32) if scales.numel() else None
-    grad_rot = torch.empty((P, 4), **f32) if rotations.numel() else None
-    grad_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp.numel() else None
+    grad_means3D = torch.empty((P, 3), **f32) if w("means3D") else None
+    grad_means2D = torch.empty((P, 3), **f32) if w("means2D") else None
+    grad_opacities = torch.empty(opacities_shape, **f32) if w("opacities") else None
+    grad_sh = torch.empty((P, 1 if raw is not None else M, 3), **f32) if sh.numel() and w("sh") else None
+    grad_colors = torch.empty((P, 3), **f32) if colors_precomp.numel() and w("colors") else None
+    grad_scales = torch.empty((P, raw[1] if raw is not None else 3), **f32) if scales.numel() and w("scales") else None
+    grad_rot = torch.empty((P, 4), **f32) if rotations.numel() and w("rotations") else None
+    grad_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp.numel() and w("cov") else None
     if P == 0:
         tau.zero_()
         res = (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau)
@@ -377,8 +397,8 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
         g = _make_gaussians(P, means3D, None, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
                             None if raw is None else (raw[0], raw[1]))
         g.opacities = means3D.data_ptr()   # opacities are not read in backward (they live in the splat records)
-        io = _BackwardIO(grad_out_color.data_ptr(), grad_out_depth.data_ptr(), grad_means3D.data_ptr(), grad_means2D.data_ptr(),
-                         grad_opacities.data_ptr(), _ptr(grad_sh), _ptr(grad_colors), _ptr(grad_scales), _ptr(grad_rot),
+        io = _BackwardIO(grad_out_color.data_ptr(), grad_out_depth.data_ptr(), _ptr(grad_means3D), _ptr(grad_means2D),
+                         _ptr(grad_opacities), _ptr(grad_sh), _ptr(grad_colors), _ptr(grad_scales), _ptr(grad_rot),
                          _ptr(grad_cov), tau.data_ptr(), _ptr(grad_rest))
         _check(_lib.g4r_backward(ctypes.byref(frame), ctypes.byref(g), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
                                  binning.data_ptr(), scratch.data_ptr(), ctypes.byref(io), stream))
@@ -426,6 +446,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img = ctx.saved_tensors
         device = means3D.device
         means3D_c = _dev_f32(means3D, device)
+        needs = ctx.needs_input_grad
+        want = dict(means3D=needs[0], means2D=needs[1], sh=needs[2], colors=needs[3], opacities=needs[4], scales=needs[5],
+                    rotations=needs[6], cov=needs[7])
         (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau) = _backward_impl(
             rs, ctx.P, means3D_c,
             _dev_f32(sh, device) if sh.numel() else sh,
@@ -433,11 +456,10 @@ class _RasterizeGaussians(torch.autograd.Function):
             _dev_f32(scales, device) if scales.numel() else scales,
             _dev_f32(rotations, device) if rotations.numel() else rotations,
             _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp,
-            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep)
+            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep, want=want)
         _debug_sync(rs, means3D)
         grad_rho = tau[:3].view(1, -1)
         grad_theta = tau[3:6].view(1, -1)
-        needs = ctx.needs_input_grad
         return (
             grad_means3D,
             grad_means2D,
@@ -566,13 +588,14 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
         device = xyz.device
         e = _empty()
         rest = _dev_f32(features_rest, device) if features_rest.numel() else None
+        needs = ctx.needs_input_grad
+        want = dict(means3D=needs[0], means2D=needs[1], sh=needs[2] or needs[3], opacities=needs[4], scales=needs[5], rotations=needs[6])
         (g_xyz, g_m2d, g_dc, _gc, g_op, g_sc, g_rot, _gcov, tau, g_rest) = _backward_impl(
             ctx.raster_settings, ctx.P, _dev_f32(xyz, device), _dev_f32(features_dc, device), e, _dev_f32(scaling_raw, device),
             _dev_f32(rotation_raw, device), e, radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth,
-            ctx.frame_keep, raw=(rest, ctx.scale_dim))
-        if g_rest is None and features_rest.numel() == 0 and ctx.needs_input_grad[3]:
+            ctx.frame_keep, raw=(rest, ctx.scale_dim), want=want)
+        if g_rest is None and features_rest.numel() == 0 and needs[3]:
             g_rest = torch.zeros_like(features_rest)
-        needs = ctx.needs_input_grad
         return (g_xyz, g_m2d, g_dc, g_rest, g_op, g_sc, g_rot,
                 tau[3:6].view(1, -1) if needs[7] else None, tau[:3].view(1, -1) if needs[8] else None, None)
 

@@ -101,16 +101,18 @@ class CudaBackend:
                               n_touched_all.data_ptr())
             cap = cap_hint
             binning = torch.empty((_lib.g4r_binning_bytes(cap),), dtype=torch.uint8, device=dev)
+            sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), dtype=torch.uint8, device=dev)
             _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), rec_all.data_ptr(), img_state.data_ptr(),
-                                           binning.data_ptr(), cap, ctypes.byref(out), stream))
+                                           binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
             N = int(_lib.g4r_wait_num_rendered(ctx))
             if N < 0:
                 _check(N)
             if N > cap:
                 cap = N
                 binning = torch.empty((_lib.g4r_binning_bytes(cap),), dtype=torch.uint8, device=dev)
+                sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), dtype=torch.uint8, device=dev)
                 _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), rec_all.data_ptr(), img_state.data_ptr(),
-                                               binning.data_ptr(), cap, ctypes.byref(out), stream))
+                                               binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
         return binning, N
 
     def composite_backward(self, rs, owner, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the hot-path benchmark (BASELINE.json metric: rasterizer fwd+bwd frames/sec @640x480, 500k Gaussians).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C2|C3sh3|C4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C2|C3sh3|C4|C3map|track]
 
 A *step* is one forward+backward pass of the differentiable rasterizer over one synthetic frame of the workload
 (tools/scenes.py; data = synthetic, seeded).  One JSON line is printed by rank 0:
@@ -321,6 +321,119 @@ def cpu_baseline(wl: Workload, min_s=10.0, max_frames=200, budget_s=25.0):
             "sample": f"{n} fwd+bwd frame(s) of workload {wl.name} (P={wl.cpu.P}, {wl.cpu.W}x{wl.cpu.H}) through oracle/g4r_oracle.c (OpenMP, f32)"}
 
 
+
+# ---------------------------------------------------------------------------------------------------------------
+# the two SLAM loop shapes BASELINE.json's configs name (config 3 "inside the mapping loop"; the tracking loop of config 5)
+# ---------------------------------------------------------------------------------------------------------------
+def run_slam_shape(args, dgr, lib, device, rank, world, barrier, ref_cuda):
+    """--workload C3map : one step = one iteration of BackEnd.map (utils/slam_backend.py:357-771): 10 views of the 500 k cloud
+                          rendered through render(), RGB-D mapping losses, ONE backward(retain_graph=True) through the 10
+                          rasterizer nodes, Adam step on the Gaussians + the 10 poses.  metric = views/s (10 per step).
+       --workload track : one step = one iteration of FrontEnd.tracking (utils/slam_frontend.py:411-448): render() of a
+                          60 k-Gaussian map with the static mask (30 k kept), RGB-D tracking loss, backward, pose Adam step,
+                          SE(3) update; only theta / rho are consumed.
+    Both through tools/slam_shapes (a restatement of the reference caller; tests/test_reference_caller.py runs the reference's
+    own file on the same objects).  e2e: the ground-truth colour + depth images of the step's views come from pinned host
+    memory every step and the loss goes back."""
+    from tools import slam_shapes as S
+    from tools.scenes import config_scene, make_scene
+    mapping = args.workload == "C3map"
+    views_n = 10 if mapping else 1
+    sc_cpu = config_scene("C3", seed=rank) if mapping else make_scene(60_000, 640, 480, sh_degree=0, seed=rank, name="track60k")
+    sc = sc_cpu.to(device)
+    g = torch.Generator().manual_seed(5 + rank)
+    dygs = torch.zeros(sc.P, dtype=torch.bool) if mapping else (torch.rand(sc.P, generator=g) < 0.5)
+    gt_host = [(torch.rand(3, sc.H, sc.W, generator=g).pin_memory(), (0.5 + 5.0 * torch.rand(1, sc.H, sc.W, generator=g)).pin_memory())
+               for _ in range(views_n)]
+    bg = torch.zeros(3, device=device)
+    pc = S.DuckGaussians.from_scene(sc, dygs=dygs.to(device))
+    base = S.DuckCamera.from_scene(sc)
+    views = [S.perturbed(base, 10 + i, rot=0.004, trans=0.01) for i in range(views_n)]
+    for v, (im, dp) in zip(views, gt_host):
+        v.original_image, v.depth_gt = im.to(device), dp.to(device)
+    render_fn = lambda *a, **k: S.render(dgr, *a, **k)
+    gopt = pc.optimizer()
+    popts = [S.pose_optimizer(v) for v in views]
+    result_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step(from_host=False):
+        if from_host:
+            for v, (im, dp) in zip(views, gt_host):
+                v.original_image, v.depth_gt = im.to(device, non_blocking=True), dp.to(device, non_blocking=True)
+        if mapping:
+            loss = S.mapping_iteration(dgr, render_fn, views, pc, bg, gopt, popts)
+        else:
+            loss = S.tracking_iteration(dgr, render_fn, views[0], pc, bg, popts[0], gopt)
+        if from_host:
+            result_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    flush = lambda: flush_buf.zero_()
+    steps = args.steps if not mapping else max(5, args.steps // 4)
+    if lib is not None:
+        lib.g4r_profile_enable(1)
+        n_st = lib.g4r_profile_stage_count()
+        lib.g4r_profile_stage_name.restype = ctypes.c_char_p
+    ms, clocks = timed_steps(step, steps, args.warmup, flush, barrier, ClockSampler(torch.cuda.current_device()) if rank == 0 else None)
+    stage = {}
+    if lib is not None:
+        ms_arr = (ctypes.c_double * n_st)()
+        cnt_arr = (ctypes.c_int64 * n_st)()
+        lib.g4r_profile_read(ms_arr, cnt_arr, 1)
+        lib.g4r_profile_enable(0)
+        stage = {lib.g4r_profile_stage_name(i).decode(): (ms_arr[i] / max(1, cnt_arr[i]), int(cnt_arr[i])) for i in range(n_st)}
+    t_total = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    total_ms = float(t_total.item())
+    value = world * steps * views_n / (total_ms / 1000.0)
+    # e2e: host ground-truth images every step, loss read back; one event pair around K steps
+    K2 = max(5, steps // 2)
+    for _ in range(3):
+        step(True)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K2):
+        step(True)
+    e1.record()
+    torch.cuda.synchronize()
+    t_h = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
+    e2e_value = world * K2 * views_n / (float(t_h.item()) / 1000.0)
+    if rank != 0:
+        return
+    h2d = sum(im.numel() * 4 + dp.numel() * 4 for im, dp in gt_host)
+    peak, peak_src = measured_peaks()
+    ms_per_step = total_ms / steps
+    visible = int((~dygs).sum())
+    line = {
+        "metric": ("mapping-loop rasterizer views/s: 10 views fwd, one backward(retain_graph=True), Adam; 500k Gaussians @640x480" if mapping
+                   else "tracking-loop iterations/s: masked render (30k of 60k Gaussians) fwd+bwd, pose Adam step @640x480"),
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: P={sc.P} Gaussians ({visible} after the static mask), {sc.W}x{sc.H}, SH degree 0, {views_n} view(s) per step, "
+                               "render() prelude + RGB-D loss + backward + Adam through tools/slam_shapes (restating utils/slam_backend.py:357-771 / "
+                               "utils/slam_frontend.py:411-448)", "parallelism": f"replicas x{world}",
+                   "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                   "api": ("UNMODIFIED reference build baseline/_ref" if ref_cuda else "this repo's drop-in") + " behind the reference's render() call shape"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(sum(c for _, c in stage.values())) if stage else 0,
+        "clocks": clocks,
+    }
+    if ref_cuda:
+        line["impl"] = "reference"
+    if stage:
+        line["kernel_ms"] = {k: round(v[0], 5) for k, v in stage.items()}
+        line["kernel_launches_per_step"] = {k: round(v[1] / (steps + args.warmup), 2) for k, v in stage.items()}
+        native = sum(v[0] * v[1] for v in stage.values()) / (steps + args.warmup)
+        line["native_kernel_ms_per_step"] = native
+        line["non_rasterizer_ms_per_step"] = ms_per_step - native
+    print(json.dumps(line))
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -364,14 +477,20 @@ def main():
             barrier()
         return
 
-    # every rank renders its own view (seed) of the workload
-    wl = Workload(args.workload, seed=rank, device=device)
     if ref_cuda:
         dgr = refload.load()
         lib = None
     else:
         import diff_gaussian_rasterization as dgr
         lib = dgr._lib
+    if args.workload in ("C3map", "track"):
+        run_slam_shape(args, dgr, lib, device, rank, world, barrier, ref_cuda)
+        if use_dist:
+            barrier()
+            dist.destroy_process_group()
+        return
+    # every rank renders its own view (seed) of the workload
+    wl = Workload(args.workload, seed=rank, device=device)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)       # > 126 MB L2
     flush = lambda: flush_buf.zero_()
 
@@ -444,7 +563,9 @@ def main():
                        "l2": "flushed between steps (256 MiB memset outside the timed events)", "timing": "CUDA events per step on the current stream, "
                        "sum over K steps, max over ranks", "api": "public GaussianRasterizer autograd API (Python -> ctypes -> C ABI)"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
-            "gpu_launches": 7 * args.steps if lib is not None else 0,
+            # launches of this library's kernels inside the timed region, counted by the library's stage profile (it covers
+            # the warm-up steps too, which run the same launches)
+            "gpu_launches": int(round(sum(v[1] for v in stage.values()) * args.steps / (args.steps + args.warmup))) if stage else 0,
             "clocks": clocks,
             "roofline_frame": {"bound": "hbm", "algorithmic_bytes": b_alg, "achieved": b_alg / (ms_per_step * 1e-3) / 1e9, "peak": peak,
                                "unit": "GB/s", "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / peak, "peak_source": peak_src,

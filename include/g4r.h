@@ -114,8 +114,10 @@ typedef struct G4RForwardOut {
 } G4RForwardOut;
 
 /* Incoming image gradients + outgoing per-Gaussian gradients (DEVICE pointers).
- * Every output is written in full (zeros for invisible Gaussians), so the caller
- * may hand in uninitialised memory.  Outputs whose input was absent may be NULL. */
+ * Every non-NULL output is written in full (zeros for invisible Gaussians), so the
+ * caller may hand in uninitialised memory.  ANY per-Gaussian output may be NULL: the
+ * gradient is then not needed (autograd's needs_input_grad -- pose tracking consumes
+ * dL_dtau only, utils/slam_frontend.py:441-448) and its stores are skipped. */
 typedef struct G4RBackwardIO {
     const float* dL_dcolor;       /* [3,H,W] */
     const float* dL_ddepth;       /* [1,H,W] */
@@ -135,7 +137,7 @@ typedef struct G4RContext G4RContext;   /* owns one pinned int + one event; one 
 
 /* ---- library / context ------------------------------------------------------------ */
 const char* g4r_last_error(void);
-int  g4r_version(void);                               /* ABI version, currently 4 */
+int  g4r_version(void);                               /* ABI version, currently 5 */
 void g4r_struct_sizes(int32_t* out5);                 /* sizeof {G4RFrame, G4RGaussians, G4RForwardOut, G4RBackwardIO, G4RLayout}: FFI self-check */
 int  g4r_context_create(G4RContext** out);
 void g4r_context_destroy(G4RContext* ctx);
@@ -143,7 +145,8 @@ void g4r_context_destroy(G4RContext* ctx);
 /* ---- scratch sizing (bytes) --------------------------------------------------------- */
 size_t g4r_geom_bytes(int32_t P);                     /* per-Gaussian splat records, saved for backward */
 size_t g4r_image_bytes(int32_t width, int32_t height);/* per-pixel final_T/n_contrib + per-tile ranges  */
-size_t g4r_binning_bytes(int64_t capacity);           /* room for `capacity` (tile,Gaussian) instances  */
+size_t g4r_binning_bytes(int64_t capacity);           /* sorted id list for `capacity` (tile,Gaussian) instances, saved for backward */
+size_t g4r_sort_scratch_bytes(int64_t capacity);      /* unsorted (depth,id) pairs: forward-only scratch, free after the call */
 size_t g4r_backward_scratch_bytes(int32_t P);         /* per-Gaussian gradient accumulators (not saved) */
 
 /* ---- forward, phase 1: projection + tile histogram + tile offsets --------------------
@@ -156,12 +159,13 @@ int g4r_forward_project(G4RContext* ctx, const G4RFrame* frame, const G4RGaussia
                         void* geom, void* img, int32_t* radii, int32_t* n_touched, void* stream);
 
 /* ---- forward, phase 2: instance scatter + per-tile depth sort + composite -------------
- * `capacity` = number of instances `binning` has room for.  If the device-side N
+ * `capacity` = number of instances `binning` (the sorted id list, saved for backward) and `sort_scratch` (the unsorted
+ * pairs, needed only until this call's kernels have run) have room for.  If the device-side N
  * turns out larger, every phase-2 kernel exits without touching memory and the
  * caller must call again with a larger buffer (see g4r_wait_num_rendered).
  * Never blocks. */
 int g4r_forward_render(G4RContext* ctx, const G4RFrame* frame, const G4RGaussians* g,
-                       void* geom, void* img, void* binning, int64_t capacity,
+                       void* geom, void* img, void* binning, void* sort_scratch, int64_t capacity,
                        const G4RForwardOut* out, void* stream);
 
 /* Waits for the event recorded by g4r_forward_project and returns N (>= 0), the
@@ -169,6 +173,12 @@ int g4r_forward_render(G4RContext* ctx, const G4RFrame* frame, const G4RGaussian
  * negative error code.  By the time phase 2 has been enqueued the event has normally
  * already fired, so the GPU is never idle waiting for the host. */
 int64_t g4r_wait_num_rendered(G4RContext* ctx);
+
+/* Forwards that run without host read-back (ctx == NULL: captured in a CUDA graph and replayed) cannot re-run phase 2 when
+ * N outgrows the capacity fixed at capture: every kernel exits untouched, the backward returns zero gradients, and the
+ * kernel that detects it records N in a per-device word.  Returns the largest such N since the last reset on the CURRENT
+ * device (0 = no overflow) or a negative error code; synchronises the device. */
+int64_t g4r_overflow_status(int reset);
 
 /* ---- backward ------------------------------------------------------------------------ */
 int g4r_backward(const G4RFrame* frame, const G4RGaussians* g,
@@ -218,7 +228,7 @@ typedef struct G4RLayout {
     size_t img_counts;      /* uint32[tiles*32]: one counter per 128-byte line */
     size_t img_header;      /* uint32[8]: [0] = N */
     size_t bin_point_list;  /* uint32[capacity] sorted Gaussian ids == reference point_list */
-    size_t bin_pairs;       /* uint2[capacity]  unsorted (depth bits, id) */
+    size_t bin_pairs;       /* uint2[capacity]  unsorted (depth bits, id), offset inside sort_scratch */
 } G4RLayout;
 int g4r_layout(int32_t P, int32_t width, int32_t height, int64_t capacity, G4RLayout* out);
 

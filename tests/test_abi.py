@@ -21,7 +21,7 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for s in ("g4r_forward_project", "g4r_forward_render", "g4r_wait_num_rendered", "g4r_backward", "g4r_mark_visible",
               "g4r_geom_bytes", "g4r_image_bytes", "g4r_binning_bytes", "g4r_backward_scratch_bytes", "g4r_context_create",
-              "g4r_context_destroy", "g4r_last_error", "g4r_version", "g4r_layout"):
+              "g4r_context_destroy", "g4r_last_error", "g4r_version", "g4r_layout", "g4r_sort_scratch_bytes", "g4r_overflow_status"):
         assert s in syms
 
 
@@ -33,17 +33,20 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_sizes():
     lib = ctypes.CDLL(LIB)
-    assert lib.g4r_version() == 4
-    for f in (lib.g4r_geom_bytes, lib.g4r_binning_bytes, lib.g4r_backward_scratch_bytes, lib.g4r_image_bytes):
+    assert lib.g4r_version() == 5
+    for f in (lib.g4r_geom_bytes, lib.g4r_binning_bytes, lib.g4r_sort_scratch_bytes, lib.g4r_backward_scratch_bytes, lib.g4r_image_bytes):
         f.restype = ctypes.c_size_t
+    lib.g4r_sort_scratch_bytes.argtypes = [ctypes.c_int64]
     lib.g4r_geom_bytes.argtypes = [ctypes.c_int32]
     lib.g4r_binning_bytes.argtypes = [ctypes.c_int64]
     lib.g4r_backward_scratch_bytes.argtypes = [ctypes.c_int32]
     lib.g4r_image_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
-    # 48-byte splat record + 1 clamp byte per Gaussian; 20 bytes per instance; 48 bytes of accumulators
+    # 48-byte splat record + 1 clamp byte per Gaussian; per instance 4 bytes saved for backward (sorted ids) + 16 bytes of
+    # forward-only sort scratch; 48 bytes of accumulators
     assert lib.g4r_geom_bytes(1000) >= 49 * 1000
     assert lib.g4r_geom_bytes(500_000) < 52 * 500_000
-    assert lib.g4r_binning_bytes(1_000_000) >= 20 * 1_000_000
+    assert 4 * 1_000_000 <= lib.g4r_binning_bytes(1_000_000) < 5 * 1_000_000       # only the sorted id list is saved
+    assert lib.g4r_sort_scratch_bytes(1_000_000) >= 16 * 1_000_000
     assert lib.g4r_backward_scratch_bytes(1000) >= 48 * 1000
     assert lib.g4r_image_bytes(640, 480) >= 8 * 640 * 480 + 16 * 1200
     assert lib.g4r_geom_bytes(0) > 0 and lib.g4r_binning_bytes(0) > 0
@@ -82,5 +85,5 @@ def test_layout_offsets_are_aligned_and_ordered():
     assert _lib.g4r_layout(1000, 640, 480, 5000, ctypes.byref(lay)) == 0
     for name, _ in _Layout._fields_:
         assert getattr(lay, name) % 16 == 0, name
-    assert lay.bin_point_list == 0 and lay.bin_pairs >= 4 * 5000
+    assert lay.bin_point_list == 0 and lay.bin_pairs == 0          # offsets inside `binning` and inside `sort_scratch`
     assert lay.img_n_contrib - lay.img_final_T >= 4 * 640 * 480

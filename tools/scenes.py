@@ -184,6 +184,128 @@ def make_scene(P: int, W: int, H: int, sh_degree: int = 0, sh_coeffs: Optional[i
     return sc
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# bit-reproducible scenes for the committed reference-output digests (tests/golden/digests_ref.json)
+# ---------------------------------------------------------------------------------------------------------------------
+def _splitmix_uniform(seed: int, stream: int, n: int) -> np.ndarray:
+    """n doubles in [0, 1) from SplitMix64 on a counter: integer arithmetic only, so every machine produces the same bits."""
+    with np.errstate(over="ignore"):
+        x = (np.arange(1, n + 1, dtype=np.uint64) + np.uint64((seed * 1000003 + stream * 7919) & 0xFFFFFFFF) * np.uint64(0x632BE59BD9B4E019))
+        x = x * np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def make_scene_exact(P: int, W: int, H: int, sh_degree: int = 0, seed: int = 0, px_min: float = 0.5, px_max: float = 3.0,
+                     name: str = "") -> Scene:
+    """Same kind of cloud as make_scene, but built ONLY from operations that IEEE-754 rounds
+    identically everywhere: integer hashing for the random numbers and element-wise + - * / sqrt in float64 (no exp / log /
+    sin / BLAS / LAPACK, whose last bit depends on the library, the vector width and the buffer alignment).  The float32
+    inputs -- and therefore the digests of the reference's outputs committed under tests/golden/ -- are reproducible on any
+    machine.  Differences to make_scene: reciprocal-uniform instead of log-uniform splat sizes, Irwin-Hall(4) instead of
+    Gaussian variates, uniform opacities (0.4 % below 1/255), a fixed rational camera rotation."""
+    stream = [0]
+
+    def U(n):
+        stream[0] += 1
+        return _splitmix_uniform(seed, stream[0], n)
+
+    def Nrm(n):                                              # Irwin-Hall(4), unit variance
+        return (U(n) + U(n) + U(n) + U(n) - 2.0) * 1.7320508075688772
+
+    fx = fy = 0.8366 * W
+    cx, cy = W / 2 + 0.1 * W / 640, H / 2 + 7.6 * H / 480
+    z = 0.5 + 5.5 * U(P)
+    n_behind = max(1, P // 100) if P >= 8 else 0
+    if n_behind:
+        z[:n_behind] = -1.0 + 1.2 * U(n_behind)
+    u = (-0.05 + 1.1 * U(P)) * W
+    v = (-0.05 + 1.1 * U(P)) * H
+    pc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], axis=1)
+    # world -> camera: p_c = R p_w + t with a rational rotation (rows (1,-4,8)/9, (8,4,1)/9, (-4,7,4)/9) and t = (0.3, -0.2, 0.25)
+    R = np.array([[1.0, -4.0, 8.0], [8.0, 4.0, 1.0], [-4.0, 7.0, 4.0]]) / 9.0
+    t = np.array([0.3, -0.2, 0.25])
+    d = pc - t
+    pw = np.stack([d[:, 0] * R[0, j] + d[:, 1] * R[1, j] + d[:, 2] * R[2, j] for j in range(3)], axis=1)      # R^T (p_c - t)
+
+    Rf, tf = R.astype(np.float32), t.astype(np.float32)
+    view = np.zeros((4, 4), np.float32)                      # viewmatrix = [R t; 0 1]^T (reference layout, Appendix A.1)
+    view[:3, :3] = Rf.T
+    view[3, :3] = tf
+    view[3, 3] = 1.0
+    znear, zfar = 0.01, 100.0
+    left = ((2 * cx - W) / W - 1.0) * W / 2.0
+    right = ((2 * cx - W) / W + 1.0) * W / 2.0
+    top = ((2 * cy - H) / H + 1.0) * H / 2.0
+    bottom = ((2 * cy - H) / H - 1.0) * H / 2.0
+    left, right, top, bottom = znear / fx * left, znear / fx * right, znear / fy * top, znear / fy * bottom
+    Pm = np.zeros((4, 4))
+    Pm[0, 0] = 2.0 * znear / (right - left)
+    Pm[1, 1] = 2.0 * znear / (top - bottom)
+    Pm[0, 2] = (right + left) / (right - left)
+    Pm[1, 2] = (top + bottom) / (top - bottom)
+    Pm[3, 2] = 1.0
+    Pm[2, 2] = zfar / (zfar - znear)
+    Pm[2, 3] = -(zfar * znear) / (zfar - znear)
+    proj_raw = Pm.T.astype(np.float32)
+    v64, p64 = view.astype(np.float64), proj_raw.astype(np.float64)
+    proj = np.zeros((4, 4))
+    for i in range(4):
+        for j in range(4):
+            acc = 0.0
+            for k in range(4):
+                acc = acc + float(v64[i, k]) * float(p64[k, j])      # plain Python doubles: one rounding per operation
+            proj[i, j] = acc
+    campos = np.array([-(float(R[0, j]) * float(t[0]) + float(R[1, j]) * float(t[1]) + float(R[2, j]) * float(t[2])) for j in range(3)])
+
+    r_px = (px_min * px_max) / (px_max - U(P * 3) * (px_max - px_min))
+    scales = (np.maximum(np.abs(z), 0.2) / fx)[:, None] * r_px.reshape(P, 3)
+    q = np.stack([Nrm(P) for _ in range(4)], axis=1)
+    qn = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
+    qn = np.where(qn > 1e-12, qn, 1.0)
+    rotations = q / qn[:, None]
+    opacities = U(P).reshape(P, 1)
+    M = (sh_degree + 1) ** 2
+    shs = np.concatenate([Nrm(P * 3).reshape(P, 1, 3), 0.1 * Nrm(P * max(M - 1, 0) * 3).reshape(P, max(M - 1, 0), 3)], axis=1)
+    grad_color = Nrm(3 * H * W).reshape(3, H, W) / (W * H)
+    grad_depth = Nrm(H * W).reshape(1, H, W) / (W * H)
+
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.float32)))
+    return Scene(name=name or f"X{P}_{W}x{H}_d{sh_degree}_s{seed}", W=W, H=H, tanfovx=W / (2.0 * fx), tanfovy=H / (2.0 * fy),
+                 bg=torch.tensor([1.0, 1.0, 1.0]), viewmatrix=f32(view), projmatrix=f32(proj), projmatrix_raw=f32(proj_raw),
+                 campos=f32(campos), sh_degree=sh_degree, scale_modifier=1.0, means3D=f32(pw), opacities=f32(opacities),
+                 shs=f32(shs), scales=f32(scales), rotations=f32(rotations), grad_color=f32(grad_color), grad_depth=f32(grad_depth),
+                 meta=dict(seed=seed, exact=True))
+
+
+EXACT_CONFIGS = {        # BASELINE.json config sizes on the bit-reproducible generator
+    "X1": dict(P=10_000, W=320, H=240, sh_degree=0),
+    "X2": dict(P=100_000, W=640, H=480, sh_degree=3),
+    "X3": dict(P=500_000, W=640, H=480, sh_degree=0),
+    "X4": dict(P=2_000_000, W=1280, H=960, sh_degree=0),
+}
+
+
+def exact_scene(name: str, seed: int = 0) -> Scene:
+    return make_scene_exact(seed=seed, name=name, **EXACT_CONFIGS[name])
+
+
+def input_digest(sc: Scene) -> str:
+    """sha256 over the bytes of every input tensor + the scalar settings."""
+    import hashlib
+    h = hashlib.sha256()
+    for k in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp", "viewmatrix", "projmatrix",
+              "projmatrix_raw", "campos", "bg", "grad_color", "grad_depth"):
+        v = getattr(sc, k)
+        if v is not None:
+            h.update(k.encode())
+            h.update(np.ascontiguousarray(v.detach().cpu().numpy()).tobytes())
+    h.update(repr((sc.W, sc.H, float(np.float32(sc.tanfovx)), float(np.float32(sc.tanfovy)), sc.sh_degree, sc.scale_modifier)).encode())
+    return h.hexdigest()
+
+
 # BASELINE.json configs (workload names used by bench.py and the tests)
 def config_scene(name: str, seed: int = 0) -> Scene:
     if name == "C1":    # 10k, 320x240, deg 0, CPU-runnable
