@@ -69,7 +69,7 @@ class _Gaussians(ctypes.Structure):
 class _ForwardOut(ctypes.Structure):
     _fields_ = [
         ("color", ctypes.c_void_p), ("depth", ctypes.c_void_p), ("opacity", ctypes.c_void_p),
-        ("radii", ctypes.c_void_p), ("n_touched", ctypes.c_void_p),
+        ("radii", ctypes.c_void_p), ("n_touched", ctypes.c_void_p), ("color_plane_stride", ctypes.c_int64),
     ]
 
 

@@ -1,38 +1,39 @@
 """Gaussian-sharded multi-GPU render (BASELINE.json config C4; no counterpart in the reference).
 
-One process per GPU (``torch.distributed``, NCCL over NVLink).  Rank r owns a contiguous shard of the Gaussians (its
-parameters, gradients and optimiser state never leave the rank) and the tiles ``t % world == r``.
+One process per GPU (``torch.distributed``, NCCL over NVLink / NVSwitch).  Rank r owns a contiguous shard of the Gaussians
+(its parameters, gradients and optimiser state never leave the rank) and the contiguous strip of tile rows
+``[r * tiles_y / world, (r + 1) * tiles_y / world)``.
 
-forward   1. project the local shard                                   (g4r_project_only)
-          2. all-gather the 48-byte splat records + radii              (NCCL all_gather, 52 B per Gaussian)
-          3. count / scan / scatter / sort / composite the OWNED tiles over all records
-                                                                         (g4r_count_tiles, g4r_forward_render)
-          4. all-reduce(sum) the image planes (non-owned pixels are 0) (NCCL all_reduce, 20 B per pixel)
-             reduce-scatter n_touched to the owning ranks
-backward  5. composite backward of the owned tiles -> partial accumulators for ALL Gaussians (g4r_backward_composite)
-          6. reduce-scatter(sum) the accumulators to the owning ranks  (NCCL reduce_scatter, 48 B per Gaussian)
-          7. per-Gaussian backward of the local shard                  (g4r_backward_gaussians); all-reduce of dL/dtau
+forward   1. project the local shard                                              g4r_project_only
+          2. pack, per destination rank, the 48-byte splat records whose tile rectangle touches that rank's strip
+             (stable compaction on the device, fixed-capacity slabs)              g4r_shard_pack
+          3. all-to-all of the slabs (equal splits: no host-side sizes; each slab's header row carries its count)
+          4. bin / sort / composite the OWNED strip over the received records, straight into an all-gather send buffer
+                                                                                  g4r_shard_unpack, g4r_count_tiles, g4r_forward_render
+          5. ONE all-gather whose payload is [image strip | n_touched of the received records | row of the count matrix]
+             -> full image on every rank (g4r_shard_assemble), n_touched summed at the owners (g4r_shard_gather), and the
+             world x world count matrix on every rank's host
+backward  6. composite backward of the owned strip -> one accumulator row per received record   g4r_backward_composite
+          7. reverse all-to-all of the rows; every owner sums the rows of its Gaussians         g4r_shard_gather
+          8. per-Gaussian backward of the local shard; all-reduce of the 6 pose-gradient floats g4r_backward_gaussians
 
-Global Gaussian ids are ``rank * Pmax + local index`` (shards padded to the largest one), which preserves the order of
-the concatenated cloud, so every tile's sorted list -- and therefore every pixel -- is identical to the single-GPU
-result.
+Nothing on this path reads a size back to the host before the frame is fully enqueued: the slab capacity per (source,
+destination) pair is speculative (high-water mark of the count matrix x 1.25, identical on all ranks because every rank sees
+the whole matrix) and the matrix is inspected after the last enqueue; a pair that outgrew the capacity makes ALL ranks redo
+the frame with a larger one -- the same scheme the single-GPU path uses for its instance capacity.
 
-``exchange="alltoall"`` replaces steps 2 and 6 by variable-size all-to-alls: rank r owns a contiguous strip of tile
-rows, every splat record travels only to the ranks whose strip its tile rectangle touches (~1.3 ranks instead of all),
-and the accumulator rows travel back the same way and are scatter-added at the owner.  Records arrive ordered by
-(source rank, local index) = global id order, so ties in depth still resolve like on one GPU.  It moves ~6x fewer
-bytes at 8 ranks, but on one NVSwitch node the extra host steps (split sizes, index build, index_add) cost more than
-the bytes save (profiles/scaling/sharded_check_C4_x*.json: 1.99 ms vs 1.76 ms at 8 GPUs), so ``"allgather"`` -- the
-variant described above, interleaved tile ownership -- is the default; ``"alltoall"`` is the one to pick when the
-exchange crosses nodes.
+Bit-exactness: the pack is a stable compaction, so inside a source's slab records keep their local order, and slabs are laid
+out by source rank: the index of a received record is monotone in the global Gaussian id.  A tile's list is sorted by
+(depth bits, index) -- the order of the single-GPU render -- so every pixel is bit-identical to it.
 
-The kernel calls go through a *backend* object so that the host logic (sharding, collectives, padding) can be
-exercised with the gloo backend on CPU by the tests, which inject a CPU backend; the product default is the CUDA library
-and there is no fallback.
+The kernel calls go through a *backend* object so that the host logic (strips, slabs, collectives, redo) can be exercised
+with the gloo backend on CPU by the tests, which inject a CPU backend built on the oracle; the product default is the CUDA
+library and there is no fallback.
 """
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import torch
 import torch.distributed as dist
@@ -40,7 +41,11 @@ import torch.distributed as dist
 from . import (_BackwardIO, _ForwardOut, _check, _context, _dev_f32, _lib, _make_frame, _make_gaussians, _ptr,
                GaussianRasterizationSettings)
 
-__all__ = ["ShardedGaussianRasterizer", "shard_bounds", "owned_tiles", "strip_bounds"]
+__all__ = ["ShardedGaussianRasterizer", "shard_bounds", "strip_bounds", "collective_bytes"]
+
+REC_FLOATS = 12       # 48-byte splat record
+ACC_FLOATS = 12       # accumulator row (10 used)
+PLANES = 5            # colour (3), depth, opacity
 
 
 def shard_bounds(P: int, world: int, rank: int):
@@ -50,98 +55,24 @@ def shard_bounds(P: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def owned_tiles(W: int, H: int, world: int, rank: int) -> torch.Tensor:
-    """Boolean mask over tiles (row-major) owned by `rank`: interleaved ownership balances the per-tile load."""
-    tiles = ((W + 15) // 16) * ((H + 15) // 16)
-    return (torch.arange(tiles) % world) == rank
+def strip_bounds(tiles_y: int, world: int, rank: int):
+    """Contiguous strip of tile rows [begin, end) owned by `rank` (same arithmetic as csrc/shard.cu make_geom)."""
+    return (rank * tiles_y) // world, ((rank + 1) * tiles_y) // world
 
 
-def _set_owner(frame, owner) -> None:
-    """owner = ("mod", rank, world) | ("rows", row_begin, row_end)"""
-    frame.tile_rank, frame.tile_world, frame.tile_row_begin, frame.tile_row_end = 0, 1, 0, 0
-    if owner[0] == "mod":
-        frame.tile_rank, frame.tile_world = int(owner[1]), int(owner[2])
-    else:
-        frame.tile_row_begin, frame.tile_row_end = int(owner[1]), int(owner[2])
+def _strip_rows(H: int, world: int):
+    """(tiles_y, max strip height in pixels)."""
+    ty = (H + 15) // 16
+    return ty, 16 * max(strip_bounds(ty, world, r)[1] - strip_bounds(ty, world, r)[0] for r in range(world))
 
 
-class CudaBackend:
-    """The kernel groups of the sharded render on the current CUDA device (C ABI of include/g4r.h)."""
-
-    def tile_rows(self, rs, P, radii, geom):
-        dev = radii.device
-        rows = torch.empty((max(P, 1), 2), dtype=torch.int32, device=dev)
-        keep = []
-        with torch.cuda.device(dev):
-            frame = _make_frame(rs, dev, 0, keep)
-            _check(_lib.g4r_tile_rows(ctypes.byref(frame), P, radii.data_ptr(), geom.data_ptr(), rows.data_ptr(),
-                                      torch.cuda.current_stream(dev).cuda_stream))
-        return rows[:P]
-
-    def project(self, rs, M, means3D, opacities, sh, colors, scales, rots, cov, rec, radii, n_touched):
-        dev = means3D.device
-        keep = []
-        with torch.cuda.device(dev):
-            frame = _make_frame(rs, dev, M, keep)
-            g = _make_gaussians(int(means3D.shape[0]), means3D, opacities, sh, colors, scales, rots, cov)
-            _check(_lib.g4r_project_only(ctypes.byref(frame), ctypes.byref(g), rec.data_ptr(), radii.data_ptr(), n_touched.data_ptr(),
-                                         torch.cuda.current_stream(dev).cuda_stream))
-
-    def render(self, rs, owner, P_all, rec_all, radii_all, n_touched_all, images, img_state, cap_hint):
-        dev = rec_all.device
-        keep = []
-        with torch.cuda.device(dev):
-            ctx = _context(dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            frame = _make_frame(rs, dev, 0, keep)
-            _set_owner(frame, owner)
-            g = _make_gaussians(P_all, rec_all, rec_all, None, None, None, None, None)
-            _check(_lib.g4r_count_tiles(ctx, ctypes.byref(frame), P_all, radii_all.data_ptr(), rec_all.data_ptr(), img_state.data_ptr(), stream))
-            out = _ForwardOut(images[0:3].data_ptr(), images[3:4].data_ptr(), images[4:5].data_ptr(), radii_all.data_ptr(),
-                              n_touched_all.data_ptr())
-            cap = cap_hint
-            binning = torch.empty((_lib.g4r_binning_bytes(cap),), dtype=torch.uint8, device=dev)
-            sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), dtype=torch.uint8, device=dev)
-            _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), rec_all.data_ptr(), img_state.data_ptr(),
-                                           binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
-            N = int(_lib.g4r_wait_num_rendered(ctx))
-            if N < 0:
-                _check(N)
-            if N > cap:
-                cap = N
-                binning = torch.empty((_lib.g4r_binning_bytes(cap),), dtype=torch.uint8, device=dev)
-                sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), dtype=torch.uint8, device=dev)
-                _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), rec_all.data_ptr(), img_state.data_ptr(),
-                                               binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
-        return binning, N
-
-    def composite_backward(self, rs, owner, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):
-        dev = rec_all.device
-        keep = []
-        with torch.cuda.device(dev):
-            frame = _make_frame(rs, dev, 0, keep)
-            _set_owner(frame, owner)
-            _check(_lib.g4r_backward_composite(ctypes.byref(frame), P_all, rec_all.data_ptr(), img_state.data_ptr(), binning.data_ptr(),
-                                               grad_color.data_ptr(), grad_depth.data_ptr(), acc_all.data_ptr(),
-                                               torch.cuda.current_stream(dev).cuda_stream))
-
-    def gaussian_backward(self, rs, M, means3D, sh, colors, scales, rots, cov, radii, rec, acc, grads: dict, tau):
-        dev = means3D.device
-        keep = []
-        with torch.cuda.device(dev):
-            frame = _make_frame(rs, dev, M, keep)
-            g = _make_gaussians(int(means3D.shape[0]), means3D, means3D, sh, colors, scales, rots, cov)
-            io = _BackwardIO(None, None, grads["means3D"].data_ptr(), grads["means2D"].data_ptr(), grads["opacities"].data_ptr(),
-                             _ptr(grads.get("sh")), _ptr(grads.get("colors")), _ptr(grads.get("scales")), _ptr(grads.get("rots")),
-                             _ptr(grads.get("cov")), tau.data_ptr())
-            _check(_lib.g4r_backward_gaussians(ctypes.byref(frame), ctypes.byref(g), radii.data_ptr(), rec.data_ptr(), acc.data_ptr(),
-                                               ctypes.byref(io), torch.cuda.current_stream(dev).cuda_stream))
-
-    def image_state_bytes(self, W, H):
-        return _lib.g4r_image_bytes(W, H)
-
-    def geom_state_bytes(self, P):
-        return _lib.g4r_geom_bytes(P)
+def collective_bytes(W: int, H: int, world: int, cap: int) -> dict:
+    """Bytes every rank SENDS per frame in each collective (what bench.py reports next to the sharded timing)."""
+    _, maxh = _strip_rows(H, world)
+    rows = cap + 1
+    return {"all_to_all_records": world * rows * REC_FLOATS * 4,
+            "all_gather_strip_ntouched_counts": (PLANES * maxh * W + world * rows + world) * 4,
+            "all_to_all_accumulators": world * rows * ACC_FLOATS * 4, "all_reduce_pose_gradient": 32}
 
 
 _lib.g4r_tile_rows.restype = ctypes.c_int
@@ -154,29 +85,159 @@ _lib.g4r_backward_composite.restype = ctypes.c_int
 _lib.g4r_backward_composite.argtypes = [ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 7
 _lib.g4r_backward_gaussians.restype = ctypes.c_int
 _lib.g4r_backward_gaussians.argtypes = [ctypes.c_void_p] * 7
+_lib.g4r_shard_scratch_bytes.restype = ctypes.c_size_t
+_lib.g4r_shard_scratch_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
+_lib.g4r_shard_pack.restype = ctypes.c_int
+_lib.g4r_shard_pack.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64] + [ctypes.c_void_p] * 5
+_lib.g4r_shard_unpack.restype = ctypes.c_int
+_lib.g4r_shard_unpack.argtypes = [ctypes.c_int32, ctypes.c_int64] + [ctypes.c_void_p] * 3
+_lib.g4r_shard_gather.restype = ctypes.c_int
+_lib.g4r_shard_gather.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+_lib.g4r_shard_assemble.restype = ctypes.c_int
+_lib.g4r_shard_assemble.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64] + [ctypes.c_void_p] * 3
 
-def _reduce_scatter_sum(out: torch.Tensor, inp: torch.Tensor, group) -> None:
-    """reduce_scatter(sum); backends without it (gloo, used by the CPU tests) fall back to all_reduce + slice."""
-    try:
-        dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group)
-    except (RuntimeError, NotImplementedError):
-        tmp = inp.clone()
-        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
-        n = out.shape[0]
-        r = dist.get_rank(group)
-        out.copy_(tmp[r * n:(r + 1) * n])
+
+class CudaBackend:
+    """The kernel groups of the sharded render on the current CUDA device (C ABI of include/g4r.h).  `fr` is the per-frame
+    bundle made by `frames()` (the ctypes camera structs are built once per frame, not once per kernel group)."""
+
+    def geom_state_bytes(self, P):
+        return _lib.g4r_geom_bytes(P)
+
+    def image_state_bytes(self, W, H):
+        return _lib.g4r_image_bytes(W, H)
+
+    def frames(self, rs, dev, M, rows):
+        keep = []
+        with torch.cuda.device(dev):
+            full = _make_frame(rs, dev, M, keep)
+            strip = _make_frame(rs, dev, 0, keep)
+        strip.tile_rank, strip.tile_world, strip.tile_row_begin, strip.tile_row_end = 0, 1, int(rows[0]), int(rows[1])
+        return dict(full=full, strip=strip, keep=keep, dev=dev, stream=torch.cuda.current_stream(dev).cuda_stream)
+
+    def project(self, fr, means3D, opacities, sh, colors, scales, rots, cov, geom, radii, n_touched):
+        with torch.cuda.device(fr["dev"]):
+            g = _make_gaussians(int(means3D.shape[0]), means3D, opacities, sh, colors, scales, rots, cov)
+            _check(_lib.g4r_project_only(ctypes.byref(fr["full"]), ctypes.byref(g), geom.data_ptr(), radii.data_ptr(), n_touched.data_ptr(),
+                                         fr["stream"]))
+
+    def pack(self, fr, P, radii, geom, world, cap, send_slab, counts, slots):
+        scratch = torch.empty((_lib.g4r_shard_scratch_bytes(P, world),), dtype=torch.uint8, device=fr["dev"])
+        with torch.cuda.device(fr["dev"]):
+            _check(_lib.g4r_shard_pack(ctypes.byref(fr["full"]), P, radii.data_ptr(), geom.data_ptr(), world, cap, send_slab.data_ptr(),
+                                       counts.data_ptr(), slots.data_ptr(), scratch.data_ptr(), fr["stream"]))
+
+    def render_strip(self, fr, rows, world, cap, recv_slab, n_touched_all, strip, W, img_state, cap_hint):
+        """Unpack + bin + sort + composite of the strip `rows` = (begin, end) over the world*(cap+1) received slots; writes the
+        strip buffer [5, maxh, W].  Returns (binning, N)."""
+        dev = fr["dev"]
+        P_all = world * (cap + 1)
+        maxh = int(strip.shape[1])
+        radii_all = torch.empty((P_all,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            ctx = _context(dev)
+            stream = fr["stream"]
+            frame = fr["strip"]
+            _check(_lib.g4r_shard_unpack(world, cap, recv_slab.data_ptr(), radii_all.data_ptr(), stream))
+            g = _make_gaussians(P_all, recv_slab, recv_slab, None, None, None, None, None)
+            _check(_lib.g4r_count_tiles(ctx, ctypes.byref(frame), P_all, radii_all.data_ptr(), recv_slab.data_ptr(), img_state.data_ptr(), stream))
+            base = strip.data_ptr() - 4 * (16 * int(rows[0])) * W              # pixel row y of the image = row y - 16*begin of the strip
+            plane = maxh * W
+            out = _ForwardOut(base, base + 4 * 3 * plane, base + 4 * 4 * plane, radii_all.data_ptr(), n_touched_all.data_ptr(), plane)
+            cap_n = cap_hint
+            u8 = dict(dtype=torch.uint8, device=dev)
+            binning = torch.empty((_lib.g4r_binning_bytes(cap_n),), **u8)
+            sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap_n),), **u8)
+            _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), recv_slab.data_ptr(), img_state.data_ptr(),
+                                           binning.data_ptr(), sort_scratch.data_ptr(), cap_n, ctypes.byref(out), stream))
+            N = int(_lib.g4r_wait_num_rendered(ctx))
+            if N < 0:
+                _check(N)
+            if N > cap_n:
+                cap_n = N
+                binning = torch.empty((_lib.g4r_binning_bytes(cap_n),), **u8)
+                sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap_n),), **u8)
+                _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), recv_slab.data_ptr(), img_state.data_ptr(),
+                                               binning.data_ptr(), sort_scratch.data_ptr(), cap_n, ctypes.byref(out), stream))
+        return binning, N
+
+    def assemble(self, fr, world, maxh, payload, rank_stride, images):
+        with torch.cuda.device(fr["dev"]):
+            _check(_lib.g4r_shard_assemble(ctypes.byref(fr["full"]), world, PLANES, maxh, rank_stride, payload.data_ptr(), images.data_ptr(),
+                                           fr["stream"]))
+
+    def host_copy(self, st, t: torch.Tensor):
+        """Start an asynchronous copy of a small device tensor to (cached) pinned host memory; returns a function that waits for
+        THAT copy only (an event recorded right behind it) and returns the host tensor -- the stream's later work keeps running."""
+        host = st.get("pinned")
+        if host is None or host.shape != t.shape:
+            host = st["pinned"] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            st["event"] = torch.cuda.Event()
+        host.copy_(t, non_blocking=True)
+        ev = st["event"]
+        ev.record(torch.cuda.current_stream(t.device))
+
+        def wait():
+            ev.synchronize()
+            return host
+        return wait
+
+    def gather(self, fr, P, world, cap, slots, acc_back=None, acc_stride=0, acc_local=None, nt_src=None, nt_offset=0, nt_stride=0, n_touched=None):
+        """acc_back: [world, stride, 12] rows; nt_src: the all-gathered payload (flat), this rank's n_touched segment of rank d's
+        payload starts at element nt_offset + d * nt_stride."""
+        nt_ptr = None if nt_src is None else nt_src.data_ptr() + 4 * nt_offset
+        with torch.cuda.device(fr["dev"]):
+            _check(_lib.g4r_shard_gather(P, world, cap, slots.data_ptr(), _ptr(acc_back), acc_stride, _ptr(acc_local), nt_ptr, nt_stride,
+                                         _ptr(n_touched), fr["stream"]))
+
+    def composite_backward(self, fr, P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all):
+        with torch.cuda.device(fr["dev"]):
+            _check(_lib.g4r_backward_composite(ctypes.byref(fr["strip"]), P_all, rec_all.data_ptr(), img_state.data_ptr(), binning.data_ptr(),
+                                               grad_color.data_ptr(), grad_depth.data_ptr(), acc_all.data_ptr(), fr["stream"]))
+
+    def gaussian_backward(self, fr, means3D, sh, colors, scales, rots, cov, radii, geom, acc, grads: dict, tau):
+        with torch.cuda.device(fr["dev"]):
+            g = _make_gaussians(int(means3D.shape[0]), means3D, means3D, sh, colors, scales, rots, cov)
+            io = _BackwardIO(None, None, grads["means3D"].data_ptr(), grads["means2D"].data_ptr(), grads["opacities"].data_ptr(),
+                             _ptr(grads.get("sh")), _ptr(grads.get("colors")), _ptr(grads.get("scales")), _ptr(grads.get("rots")),
+                             _ptr(grads.get("cov")), tau.data_ptr())
+            _check(_lib.g4r_backward_gaussians(ctypes.byref(fr["full"]), ctypes.byref(g), radii.data_ptr(), geom.data_ptr(), acc.data_ptr(),
+                                               ctypes.byref(io), fr["stream"]))
 
 
-REC_FLOATS = 12       # 48-byte splat record
-ACC_FLOATS = 12       # accumulator row (10 used)
+# per (device, W, H, world) state shared by the per-call rasterizer objects: slab capacity per rank pair and the instance capacity
+_shard_lock = threading.Lock()
+_shard_state: dict = {}
+
+
+def _state(key) -> dict:
+    with _shard_lock:
+        st = _shard_state.get(key)
+        if st is None:
+            st = _shard_state[key] = dict(pair_hint=0, n_hint=0, P=None, Pmax=None, cap=None, redos=0)
+        return st
+
+
+def last_capacity(device, W: int, H: int, world: int):
+    """Slab capacity (records per rank pair) the most recent frame of this shape ran with (bench.py reports bytes from it)."""
+    return _state((str(torch.device(device)), W, H, world)).get("cap")
 
 
 class _ShardedRasterize(torch.autograd.Function):
+    """Strip ownership + fixed-capacity all-to-all of splat records (forward) and accumulator rows (backward).  Two
+    collectives per direction: forward = all-to-all of the slabs + ONE all-gather whose payload is this rank's image strip,
+    the n_touched of the records it received and its row of the count matrix; backward = reverse all-to-all of the
+    accumulator rows + the 6-float pose-gradient all-reduce."""
+
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs, group, backend):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         dev = means3D.device
         H, W = int(rs.image_height), int(rs.image_width)
+        tiles_y, maxh = _strip_rows(H, world)
+        if world > tiles_y:
+            raise ValueError(f"{world} ranks but only {tiles_y} tile rows: a rank would own an empty strip")
         P = int(means3D.shape[0])
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -188,201 +249,101 @@ class _ShardedRasterize(torch.autograd.Function):
         rotations = _dev_f32(rotations, dev) if rotations.numel() else rotations
         cov3Ds_precomp = _dev_f32(cov3Ds_precomp, dev) if cov3Ds_precomp.numel() else cov3Ds_precomp
         M = int(sh.size(1)) if sh.numel() else 0
+        st = _state((str(dev), W, H, world))
 
-        # shard sizes -> padded global index space
-        sizes = torch.tensor([P], dtype=torch.int64, device=dev)
-        all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
-        dist.all_gather(all_sizes, sizes, group=group)
-        Pmax = max(1, int(max(int(s.item()) for s in all_sizes)))
-        P_all = world * Pmax
+        # shard sizes: the largest one bounds the slab capacity of the very first frame (cached until the model is resized)
+        if st["P"] != P or st["Pmax"] is None:
+            sizes = torch.tensor([P], dtype=torch.int64, device=dev)
+            all_sizes = torch.empty((world,), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_sizes.view(-1), sizes.view(-1), group=group)
+            st["Pmax"], st["P"] = max(1, int(all_sizes.max().item())), P
+        Pmax = st["Pmax"]
 
-        # 1. local projection into a padded slab; padding rows keep radius 0 (invisible)
-        rec_local = torch.zeros((Pmax, REC_FLOATS), **f32)
-        radii_local = torch.zeros((Pmax,), **i32)
-        ntouch_local = torch.zeros((Pmax,), **i32)
-        # local geometry state: records first (the all-gathered slab), the per-Gaussian clamp bytes behind them
-        geom_local = torch.zeros((max(Pmax * 48, backend.geom_state_bytes(max(P, 1))) + 256,), dtype=torch.uint8, device=dev)
-        if P > 0:
-            backend.project(rs, M, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, geom_local, radii_local,
-                            ntouch_local)
-        rec_local = geom_local[: Pmax * 48].view(torch.float32).view(Pmax, REC_FLOATS)
-
-        # 2. all-gather records and radii
-        rec_all = torch.empty((P_all, REC_FLOATS), **f32)
-        radii_all = torch.empty((P_all,), **i32)
-        dist.all_gather_into_tensor(rec_all, rec_local.contiguous(), group=group)
-        dist.all_gather_into_tensor(radii_all, radii_local, group=group)
-
-        # 3. owned tiles: count / scan / scatter / sort / composite
-        images = torch.zeros((5, H, W), **f32)                      # colour(3) depth(1) opacity(1); zeros outside owned tiles
-        ntouch_all = torch.zeros((P_all,), **i32)
-        img_state = torch.empty((backend.image_state_bytes(W, H),), dtype=torch.uint8, device=dev)
-        cap = max(4096, int(1.5 * 4 * P_all / world))
-        binning, N = backend.render(rs, ("mod", rank, world), P_all, rec_all, radii_all, ntouch_all, images, img_state, cap)
-
-        # 4. image all-reduce, n_touched reduce-scatter
-        dist.all_reduce(images, op=dist.ReduceOp.SUM, group=group)
-        ntouch_out = torch.empty((Pmax,), **i32)
-        _reduce_scatter_sum(ntouch_out, ntouch_all, group)
-
-        ctx.rs, ctx.group, ctx.backend, ctx.P, ctx.Pmax, ctx.M = rs, group, backend, P, Pmax, M
-        ctx.opacities_shape = tuple(opacities.shape)
-        ctx.binning = binning            # opaque to this layer (a byte tensor for the CUDA backend)
-        ctx.save_for_backward(means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, rec_all, img_state)
-        radii = radii_local[:P].clone()
-        n_touched = ntouch_out[:P].clone()
-        ctx.mark_non_differentiable(radii, n_touched)
-        return images[0:3].clone(), radii, images[3:4].clone(), images[4:5].clone(), n_touched
-
-    @staticmethod
-    def backward(ctx, grad_color, grad_radii, grad_depth, grad_opacity, grad_ntouched):
-        means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, rec_all, img_state = ctx.saved_tensors
-        binning = ctx.binning
-        rs, group, backend, P, Pmax, M = ctx.rs, ctx.group, ctx.backend, ctx.P, ctx.Pmax, ctx.M
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        dev = means3D.device
-        f32 = dict(dtype=torch.float32, device=dev)
-        P_all = world * Pmax
-        grad_color = _dev_f32(grad_color, dev)
-        grad_depth = _dev_f32(grad_depth, dev)
-
-        # 5. + 6. partial accumulators of the owned tiles -> owners of the Gaussians
-        acc_all = torch.empty((P_all, ACC_FLOATS), **f32)
-        backend.composite_backward(rs, ("mod", rank, world), P_all, rec_all, img_state, binning, grad_color, grad_depth, acc_all)
-        acc_local = torch.empty((Pmax, ACC_FLOATS), **f32)
-        _reduce_scatter_sum(acc_local, acc_all, group)
-
-        # 7. per-Gaussian backward of the local shard
-        grads = dict(means3D=torch.empty((P, 3), **f32), means2D=torch.empty((P, 3), **f32), opacities=torch.empty(ctx.opacities_shape, **f32))
-        if sh.numel():
-            grads["sh"] = torch.empty((P, M, 3), **f32)
-        if colors_precomp.numel():
-            grads["colors"] = torch.empty((P, 3), **f32)
-        if scales.numel():
-            grads["scales"] = torch.empty((P, 3), **f32)
-            grads["rots"] = torch.empty((P, 4), **f32)
-        if cov3Ds_precomp.numel():
-            grads["cov"] = torch.empty((P, 6), **f32)
-        tau = torch.zeros((8,), **f32)
-        if P > 0:
-            backend.gaussian_backward(rs, M, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local,
-                                      acc_local, grads, tau)
-        dist.all_reduce(tau, op=dist.ReduceOp.SUM, group=group)
-        needs = ctx.needs_input_grad
-        return (grads["means3D"], grads["means2D"], grads.get("sh"), grads.get("colors"), grads["opacities"], grads.get("scales"),
-                grads.get("rots"), grads.get("cov"), tau[3:6].view(1, -1) if needs[8] else None, tau[:3].view(1, -1) if needs[9] else None,
-                None, None, None)
-
-
-def strip_bounds(tiles_y: int, world: int, rank: int):
-    """Contiguous strip of tile rows [begin, end) owned by `rank`."""
-    return (rank * tiles_y) // world, ((rank + 1) * tiles_y) // world
-
-
-def _all_to_all_rows(send: torch.Tensor, send_counts, recv_counts, group) -> torch.Tensor:
-    """Variable-size all-to-all of the rows of a 2-D tensor."""
-    recv = torch.empty((int(sum(recv_counts)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
-    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
-                           input_split_sizes=[int(c) for c in send_counts], group=group)
-    return recv
-
-
-class _ShardedRasterizeA2A(torch.autograd.Function):
-    """Strip ownership + variable-size all-to-all of splat records (forward) and accumulator rows (backward)."""
-
-    @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs, group, backend):
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        dev = means3D.device
-        H, W = int(rs.image_height), int(rs.image_width)
-        tiles_y = (H + 15) // 16
-        P = int(means3D.shape[0])
-        f32 = dict(dtype=torch.float32, device=dev)
-        i32 = dict(dtype=torch.int32, device=dev)
-        means3D = _dev_f32(means3D, dev)
-        opacities = _dev_f32(opacities, dev)
-        sh = _dev_f32(sh, dev) if sh.numel() else sh
-        colors_precomp = _dev_f32(colors_precomp, dev) if colors_precomp.numel() else colors_precomp
-        scales = _dev_f32(scales, dev) if scales.numel() else scales
-        rotations = _dev_f32(rotations, dev) if rotations.numel() else rotations
-        cov3Ds_precomp = _dev_f32(cov3Ds_precomp, dev) if cov3Ds_precomp.numel() else cov3Ds_precomp
-        M = int(sh.size(1)) if sh.numel() else 0
-
+        rb, re_ = strip_bounds(tiles_y, world, rank)
+        fr = backend.frames(rs, dev, M, (rb, re_))
         # 1. local projection
         Pp = max(P, 1)
-        geom_local = torch.zeros((max(Pp * 48, backend.geom_state_bytes(Pp)) + 256,), dtype=torch.uint8, device=dev)
-        radii_local = torch.zeros((Pp,), **i32)
-        ntouch_local = torch.zeros((Pp,), **i32)
+        geom_local = torch.empty((backend.geom_state_bytes(Pp),), dtype=torch.uint8, device=dev)
+        radii_local = torch.zeros((Pp,), **i32) if P == 0 else torch.empty((Pp,), **i32)
+        ntouch_local = torch.zeros((Pp,), **i32) if P == 0 else torch.empty((Pp,), **i32)
         if P > 0:
-            backend.project(rs, M, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, geom_local, radii_local,
-                            ntouch_local)
-        rec_local = geom_local[: Pp * 48].view(torch.float32).view(Pp, REC_FLOATS)
+            backend.project(fr, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, geom_local, radii_local, ntouch_local)
+        strip_elems = PLANES * maxh * W
+        for _attempt in range(3):
+            cap = min(Pmax, int(st["pair_hint"] * 1.25) + 256) if st["pair_hint"] > 0 else Pmax
+            slab_rows = cap + 1                                             # + the header row that carries the count
+            # all-gather payload of this rank: [image strip | n_touched of the received records | its row of the count matrix]
+            nt_elems = world * slab_rows
+            payload_elems = strip_elems + nt_elems + world
+            payload = torch.empty((payload_elems,), **f32)
+            payload[strip_elems:strip_elems + nt_elems].zero_()
+            strip = payload[:strip_elems].view(PLANES, maxh, W)
+            ntouch_all = payload[strip_elems:strip_elems + nt_elems].view(torch.int32)
+            counts = payload[strip_elems + nt_elems:].view(torch.int32)
+            # 2. pack per destination (writes the slabs, their headers, `counts` and the slot table)
+            send_slab = torch.empty((world, slab_rows, REC_FLOATS), **f32)
+            slots = torch.empty((world, Pp), **i32)
+            backend.pack(fr, P, radii_local, geom_local, world, cap, send_slab, counts, slots)
+            # 3. exchange the slabs
+            recv_slab = torch.empty((world, slab_rows, REC_FLOATS), **f32)
+            dist.all_to_all_single(recv_slab, send_slab, group=group)
+            # 4. owned strip
+            img_state = torch.empty((backend.image_state_bytes(W, H),), dtype=torch.uint8, device=dev)
+            cap_n = int(st["n_hint"] * 1.25) + 4096 if st["n_hint"] > 0 else max(4096, 6 * cap)
+            binning, N = backend.render_strip(fr, (rb, re_), world, cap, recv_slab, ntouch_all, strip, W, img_state, cap_n)
+            st["n_hint"] = max(N, int(st["n_hint"] * 0.95))
+            # 5. one all-gather: strips -> full image on every rank, n_touched -> owners, count matrix -> everybody's host
+            gathered = torch.empty((world, payload_elems), **f32)
+            dist.all_gather_into_tensor(gathered.view(-1), payload, group=group)
+            counts_on_host = backend.host_copy(st, gathered[:, strip_elems + nt_elems:].view(torch.int32))
+            images = torch.empty((PLANES, H, W), **f32)
+            backend.assemble(fr, world, maxh, gathered, payload_elems, images)
+            if P > 0:
+                backend.gather(fr, P, world, cap, slots, nt_src=gathered, nt_offset=strip_elems + rank * slab_rows, nt_stride=payload_elems,
+                               n_touched=ntouch_local)
+            # everything is enqueued: now look at the count matrix (identical on all ranks -> identical decision)
+            worst = int(counts_on_host().max())
+            st["pair_hint"] = max(worst, int(st["pair_hint"] * 0.95))
+            st["cap"] = cap
+            if worst <= cap:
+                break
+            st["redos"] += 1                 # some pair's slab was too small: every rank redoes the frame with the new hint
+        else:
+            raise RuntimeError("sharded render: slab capacity kept overflowing")
 
-        # 2. destinations: every rank whose strip of tile rows intersects the splat's rectangle
-        rows = backend.tile_rows(rs, P, radii_local, geom_local) if P > 0 else torch.zeros((0, 2), **i32)
-        begins = torch.tensor([strip_bounds(tiles_y, world, r)[0] for r in range(world)], **i32).view(world, 1)
-        ends = torch.tensor([strip_bounds(tiles_y, world, r)[1] for r in range(world)], **i32).view(world, 1)
-        first, last = rows[:, 0].view(1, -1), rows[:, 1].view(1, -1)
-        touch = (first < ends) & (last >= begins) & (last >= first)                  # (world, P)
-        dest_src = torch.nonzero(touch)                                              # sorted by destination, then local index
-        send_idx = dest_src[:, 1].contiguous()
-        send_counts = touch.sum(dim=1).to(torch.int64)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts, group=group)
-        send_counts_l, recv_counts_l = send_counts.tolist(), recv_counts.tolist()
-
-        # 3. exchange the 48-byte records; the radius rides in the record's spare slot
-        send_rec = rec_local[send_idx].clone()
-        send_rec[:, 11] = radii_local[send_idx].view(torch.float32) if send_idx.numel() else send_rec[:, 11]
-        rec_recv = _all_to_all_rows(send_rec, send_counts_l, recv_counts_l, group)
-        P_recv = int(rec_recv.shape[0])
-        rec_work = rec_recv if P_recv > 0 else torch.zeros((1, REC_FLOATS), **f32)
-        radii_recv = rec_work[:, 11].contiguous().view(torch.int32)
-
-        # 4. owned strip: count / scan / scatter / sort / composite over the received records
-        rb, re_ = strip_bounds(tiles_y, world, rank)
-        images = torch.zeros((5, H, W), **f32)
-        ntouch_recv = torch.zeros((max(P_recv, 1),), **i32)
-        img_state = torch.empty((backend.image_state_bytes(W, H),), dtype=torch.uint8, device=dev)
-        cap = max(4096, int(6 * max(P_recv, 1)))
-        binning, N = backend.render(rs, ("rows", rb, re_), P_recv, rec_work, radii_recv, ntouch_recv, images, img_state, cap)
-
-        # 5. image all-reduce (every pixel has exactly one owner), n_touched back to the owners of the Gaussians
-        dist.all_reduce(images, op=dist.ReduceOp.SUM, group=group)
-        ntouch_back = _all_to_all_rows(ntouch_recv[:P_recv].view(-1, 1), recv_counts_l, send_counts_l, group).view(-1)
-        if send_idx.numel():
-            ntouch_local.index_add_(0, send_idx, ntouch_back)
-
-        ctx.rs, ctx.group, ctx.backend, ctx.P, ctx.M, ctx.P_recv = rs, group, backend, P, M, P_recv
-        ctx.counts = (send_counts_l, recv_counts_l)
-        ctx.owner = ("rows", rb, re_)
+        ctx.rs, ctx.group, ctx.backend, ctx.P, ctx.M = rs, group, backend, P, M
+        ctx.world, ctx.cap, ctx.fr = world, cap, fr
         ctx.opacities_shape = tuple(opacities.shape)
-        ctx.binning = binning
-        ctx.save_for_backward(means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, rec_work, img_state, send_idx)
-        radii = radii_local[:P].clone()
-        n_touched = ntouch_local[:P].clone()
+        ctx.binning = binning            # opaque to this layer (a byte tensor for the CUDA backend)
+        ctx.gathered = gathered          # keeps the n_touched segment alive until the gather kernel has run (stream-ordered anyway)
+        ctx.save_for_backward(means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, recv_slab, img_state, slots)
+        radii = radii_local[:P]
+        n_touched = ntouch_local[:P]
         ctx.mark_non_differentiable(radii, n_touched)
-        return images[0:3].clone(), radii, images[3:4].clone(), images[4:5].clone(), n_touched
+        return images[0:3], radii, images[3:4], images[4:5], n_touched
 
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_opacity, grad_ntouched):
-        means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, rec_work, img_state, send_idx = ctx.saved_tensors
-        rs, group, backend, P, M, P_recv = ctx.rs, ctx.group, ctx.backend, ctx.P, ctx.M, ctx.P_recv
-        send_counts_l, recv_counts_l = ctx.counts
+        means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local, recv_slab, img_state, slots = ctx.saved_tensors
+        group, backend, P, M, fr = ctx.group, ctx.backend, ctx.P, ctx.M, ctx.fr
+        world, cap = ctx.world, ctx.cap
+        ctx.gathered = None
         dev = means3D.device
         f32 = dict(dtype=torch.float32, device=dev)
         grad_color = _dev_f32(grad_color, dev)
         grad_depth = _dev_f32(grad_depth, dev)
+        slab_rows = cap + 1
 
-        # composite backward of the owned strip -> one accumulator row per received record -> back to the owners
-        acc_recv = torch.zeros((max(P_recv, 1), ACC_FLOATS), **f32)
-        if P_recv > 0:
-            backend.composite_backward(rs, ctx.owner, P_recv, rec_work, img_state, ctx.binning, grad_color, grad_depth, acc_recv)
-        acc_back = _all_to_all_rows(acc_recv[:P_recv], recv_counts_l, send_counts_l, group)
-        acc_local = torch.zeros((max(P, 1), ACC_FLOATS), **f32)
-        if send_idx.numel():
-            acc_local.index_add_(0, send_idx, acc_back)
+        # 6. + 7. accumulator rows of the received records -> back to the owners -> summed per Gaussian
+        acc_all = torch.empty((world, slab_rows, ACC_FLOATS), **f32)
+        backend.composite_backward(fr, world * slab_rows, recv_slab, img_state, ctx.binning, grad_color, grad_depth, acc_all)
+        acc_back = torch.empty((world, slab_rows, ACC_FLOATS), **f32)
+        dist.all_to_all_single(acc_back, acc_all, group=group)
+        acc_local = torch.empty((max(P, 1), ACC_FLOATS), **f32)
+        if P > 0:
+            backend.gather(fr, P, world, cap, slots, acc_back=acc_back, acc_stride=slab_rows, acc_local=acc_local)
 
+        # 8. per-Gaussian backward of the local shard
         grads = dict(means3D=torch.empty((P, 3), **f32), means2D=torch.empty((P, 3), **f32), opacities=torch.empty(ctx.opacities_shape, **f32))
         if sh.numel():
             grads["sh"] = torch.empty((P, M, 3), **f32)
@@ -395,10 +356,11 @@ class _ShardedRasterizeA2A(torch.autograd.Function):
             grads["cov"] = torch.empty((P, 6), **f32)
         tau = torch.zeros((8,), **f32)
         if P > 0:
-            backend.gaussian_backward(rs, M, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local,
+            backend.gaussian_backward(fr, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii_local, geom_local,
                                       acc_local, grads, tau)
-        dist.all_reduce(tau, op=dist.ReduceOp.SUM, group=group)
         needs = ctx.needs_input_grad
+        if needs[8] or needs[9]:
+            dist.all_reduce(tau, op=dist.ReduceOp.SUM, group=group)
         return (grads["means3D"], grads["means2D"], grads.get("sh"), grads.get("colors"), grads["opacities"], grads.get("scales"),
                 grads.get("rots"), grads.get("cov"), tau[3:6].view(1, -1) if needs[8] else None, tau[:3].view(1, -1) if needs[9] else None,
                 None, None, None)
@@ -409,14 +371,13 @@ class ShardedGaussianRasterizer(torch.nn.Module):
     full image on every rank and the local ``radii`` / ``n_touched``.  The image gradients handed to backward must be
     identical on all ranks (every rank evaluates the loss on the full image)."""
 
-    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "allgather"):
+    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "alltoall"):
         super().__init__()
-        if exchange not in ("alltoall", "allgather"):
-            raise ValueError("exchange must be 'alltoall' or 'allgather'")
+        if exchange != "alltoall":
+            raise ValueError("exchange must be 'alltoall' (the all-gather variant of round 1 moved world x more bytes and was removed)")
         self.raster_settings = raster_settings
         self.group = group
         self.backend = backend if backend is not None else CudaBackend()
-        self.exchange = exchange
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
                 theta=None, rho=None):
@@ -425,6 +386,5 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         e = lambda t: torch.Tensor([]) if t is None else t
-        fn = _ShardedRasterizeA2A if self.exchange == "alltoall" else _ShardedRasterize
-        return fn.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
-                        e(theta), e(rho), self.raster_settings, self.group, self.backend)
+        return _ShardedRasterize.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
+                                       e(theta), e(rho), self.raster_settings, self.group, self.backend)

@@ -527,6 +527,26 @@ def main():
         dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
     e2e_value = world * K2 / (float(t_h.item()) / 1000.0)
 
+    # ---- Gaussian-sharded render of ONE large frame (BASELINE.json config 4; N > 1 only) -----------------------------------
+    # The headline `value` above is the C3 frame replicated over independent views (no data-path collective).  The path
+    # north_star shards is the 2 M-Gaussian 1280x960 mapping render: every rank owns a shard of the Gaussians and a strip of
+    # tile rows; NCCL all-to-all of splat records, all-gather of image strips, reverse all-to-all of gradient rows.
+    sharded_rec = None
+    if use_dist and lib is not None and args.workload == "C3":
+        try:
+            from tools.sharded_check import measure, passed
+            rep = measure("X4", 10, device, rank, world, local_rank)
+            reps = [None] * world
+            dist.all_gather_object(reps, rep)
+            sharded_rec = dict(reps[0])
+            sharded_rec["parity_on_every_rank"] = all(passed(r) for r in reps)
+            sharded_rec["note"] = ("X4 = 2 M Gaussians, 1280x960, SH degree 0 on the bit-reproducible generator (tools.scenes.exact_scene); "
+                                   "ms = fwd+bwd through ShardedGaussianRasterizer, CUDA events, max over ranks; single-GPU ms = the same "
+                                   "frame through GaussianRasterizer on one GPU of this box")
+        except Exception as exc:                      # the replica numbers stand on their own
+            sys.stderr.write(f"sharded leg failed: {exc!r}\n")
+            sharded_rec = {"error": repr(exc)[:300]}
+
     graph_ms, graph_overflow = (None, None)
     if lib is not None and rank == 0 and not use_dist:
         try:
@@ -604,6 +624,8 @@ def main():
                 ach_issue = warp_inst / (kt[dom] * 1e-3)
                 line["issue_roofline"] = {"kernel": dom, "warp_instructions_per_launch": warp_inst, "achieved": ach_issue / 1e9,
                                           "peak": peak_issue / 1e9, "unit": "G warp-instructions/s", "frac": ach_issue / peak_issue}
+        if sharded_rec is not None:
+            line["sharded"] = sharded_rec
         if graph_ms is not None:
             line["cuda_graph"] = {"value": 1000.0 / graph_ms, "unit": "frames/s", "ms_per_step": graph_ms, "capacity_overflow": graph_overflow,
                                   "note": "same step (fwd + loss + bwd through the public API) captured once with torch.cuda.graph and replayed; "

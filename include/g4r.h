@@ -111,6 +111,9 @@ typedef struct G4RForwardOut {
     float*   opacity;             /* [1,H,W] */
     int32_t* radii;               /* [P]     */
     int32_t* n_touched;           /* [P]     */
+    int64_t  color_plane_stride;  /* floats between the three colour planes; 0 = width * height.  The sharded render lets a rank
+                                   * composite its strip of tile rows straight into an all-gather send buffer [5][rows][W]: it
+                                   * passes pointers offset by -first_row * W and the strip's plane stride. */
 } G4RForwardOut;
 
 /* Incoming image gradients + outgoing per-Gaussian gradients (DEVICE pointers).
@@ -186,17 +189,40 @@ int g4r_backward(const G4RFrame* frame, const G4RGaussians* g,
                  void* scratch, const G4RBackwardIO* io, void* stream);
 
 /* ---- building blocks of the Gaussian-sharded multi-GPU render ------------
- * Each rank projects its own shard (g4r_project_only), the 48-byte splat records + radii of all shards are all-gathered
- * by the caller (NCCL), and every rank bins / sorts / composites only the tiles it owns (frame->tile_rank/tile_world):
- *   g4r_count_tiles  : per-owned-tile histogram over ALL gathered records + tile scan + async copy of N (like phase 1)
- *   g4r_forward_render (above) then scatters / sorts / composites the owned tiles; other pixels are left untouched
- *   g4r_backward_composite : zeroes `acc` ([P_all,12] floats) and accumulates the owned tiles' screen-space gradients
- *   g4r_backward_gaussians : per-Gaussian backward of one shard from its (reduce-scattered) accumulator rows
- * g4r_backward == g4r_backward_composite + g4r_backward_gaussians on one GPU. */
-/* First / last tile row touched by each Gaussian (rows[2*i], rows[2*i+1]; 1,0 when invisible): the destinations of the
- * all-to-all exchange.  Same rectangle arithmetic as the binning kernels. */
-int g4r_tile_rows(const G4RFrame* frame, int32_t P, const int32_t* radii, const void* geom, int32_t* rows, void* stream);
+ * One process per GPU.  Rank r owns a contiguous shard of the Gaussians and the strip of tile rows
+ * [r*tiles_y/world, (r+1)*tiles_y/world).  Per frame and rank (all enqueued on `stream`, no host synchronisation):
+ *   g4r_project_only      project the local shard (48-byte splat records + radii)
+ *   g4r_shard_pack        per destination rank d, stably compact the records whose tile rectangle touches d's strip into
+ *                         send_slab[d][0..counts[d]) (fixed capacity `cap` per pair; the radius rides in the record's spare
+ *                         slot; the count in the slab's header row) and write slots[d][i] = position of Gaussian i in slab d, or -1
+ *   (caller)              all-to-all of the slabs (NCCL, equal splits)
+ *   g4r_shard_unpack      radii of all world*(cap+1) received slots (0 for unused ones)
+ *   g4r_count_tiles + g4r_forward_render   bin / sort / composite the OWNED strip over the received records (frame->tile_row_*),
+ *                         writing into a strip buffer through G4RForwardOut.color_plane_stride
+ *   (caller)              all-gather of the strips; g4r_shard_assemble builds the [planes,H,W] images
+ *   g4r_backward_composite   accumulator rows of the received records; (caller) reverse all-to-all
+ *   g4r_shard_gather      acc_local[i] = sum of the rows that came back for Gaussian i (same for n_touched)
+ *   g4r_backward_gaussians   per-Gaussian backward of the local shard; (caller) all-reduce of dL_dtau
+ * g4r_backward == g4r_backward_composite + g4r_backward_gaussians on one GPU.  counts[d] > cap means records were dropped:
+ * the caller (which sees the count matrix on the host after everything is enqueued) redoes the frame with a larger cap. */
 int g4r_project_only(const G4RFrame* frame, const G4RGaussians* g, void* geom, int32_t* radii, int32_t* n_touched, void* stream);
+size_t g4r_shard_scratch_bytes(int32_t P, int32_t world);
+int g4r_shard_pack(const G4RFrame* frame, int32_t P, const int32_t* radii, const void* geom, int32_t world, int64_t cap,
+                   void* send_slab, int32_t* counts, int32_t* slots, void* scratch, void* stream);
+/* Slabs are [world][cap + 1] records: row `cap` of slab d is its header {count, 0, ...}, so the counts travel inside the
+ * all-to-all.  Received slots are numbered j = s * (cap + 1) + k; g4r_shard_unpack writes radii_all[world * (cap + 1)]. */
+int g4r_shard_unpack(int32_t world, int64_t cap, const void* recv_slab, int32_t* radii_all, void* stream);
+/* acc_back / n_touched_back hold, for destination d, the rows that came back for the records this rank sent to d, starting at
+ * row (element) d * stride: stride = cap + 1 rows after the reverse all-to-all, or the payload size when the data arrives
+ * inside the strips' all-gather. */
+int g4r_shard_gather(int32_t P, int32_t world, int64_t cap, const int32_t* slots, const void* acc_back, int64_t acc_stride_rows,
+                     void* acc_local, const int32_t* n_touched_back, int64_t n_touched_stride, int32_t* n_touched, void* stream);
+/* strips: for rank r, [planes][maxh][W] floats starting at strips + r * rank_stride. */
+int g4r_shard_assemble(const G4RFrame* frame, int32_t world, int32_t planes, int32_t maxh, int64_t rank_stride, const float* strips,
+                       float* images, void* stream);
+/* First / last tile row touched by each Gaussian (rows[2*i], rows[2*i+1]; 1,0 when invisible).  Same rectangle arithmetic as
+ * the binning kernels (inspection / tests). */
+int g4r_tile_rows(const G4RFrame* frame, int32_t P, const int32_t* radii, const void* geom, int32_t* rows, void* stream);
 int g4r_count_tiles(G4RContext* ctx, const G4RFrame* frame, int32_t P_all, const int32_t* radii_all, const void* geom_all,
                     void* img, void* stream);
 int g4r_backward_composite(const G4RFrame* frame, int32_t P_all, const void* geom_all, const void* img, const void* binning,

@@ -22,7 +22,9 @@ for stage in "$@"; do
     ncuall)   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'project_kernel|tile_scan|scatter_kernel|tile_sort|composite|gaussian_backward' -s 21 -c 7 -o gpurun_out/prof_all -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncuall.log 2>&1; echo "rc=$?"
               # summarise on the box so that a bench stage later in this session reports this capture's DRAM traffic
               python tools/ncu_summary.py gpurun_out/prof_all.ncu-rep "${G4R_TAG:-r01_v7}" && cp profiles/ncu_traffic.json profiles/${G4R_TAG:-r01_v7}_ncu_summary.md gpurun_out/ ;;
-    sharded2) for wl in C2 C4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py --workload $wl > gpurun_out/sharded_$wl.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_$wl.log; done ;;
+    sharded2) for wl in small X2 X4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py --workload $wl > gpurun_out/sharded_$wl.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_$wl.log | cut -c1-1800; done ;;
+    shardedN) n=${G4R_NGPU:-8}; for wl in X4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 tools/sharded_check.py --workload $wl > gpurun_out/sharded_${wl}_x$n.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_${wl}_x$n.log | cut -c1-2500; done ;;
+    benchN)   n=${G4R_NGPU:-8}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $n --steps 100 > gpurun_out/bench_x$n.json 2> gpurun_out/bench_x$n.err; echo "rc=$?"; cat gpurun_out/bench_x$n.json | cut -c1-4000; tail -5 gpurun_out/bench_x$n.err ;;
     bench2)   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 100 --no-cpu-baseline > gpurun_out/bench_x2.json 2> gpurun_out/bench_x2.err; echo "rc=$?"; cat gpurun_out/bench_x2.json ;;
     shard8)   for n in 2 4 8; do
                 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n tools/sharded_check.py --workload C4 > gpurun_out/sharded_C4_x$n.log 2>&1; echo "sharded C4 x$n rc=$?"; tail -2 gpurun_out/sharded_C4_x$n.log | cut -c1-1500
