@@ -63,11 +63,30 @@ void g4r_stage_end(int stage, cudaStream_t s) {
 }
 
 struct G4RContext {
-    int32_t* host_n;        // pinned
+    int32_t* host_n;        // pinned: [0..3] instance count read-back, [4..4+16*16) the sharded render's count matrix
     cudaEvent_t ev;
+    cudaEvent_t ev_matrix;
     bool pending;
+    bool matrix_pending;
     int renders_since_project;   // > 0: the scatter cursors of the current image state are dirty
 };
+#define CTX_MATRIX_OFFSET 4
+#define CTX_PINNED_INTS (CTX_MATRIX_OFFSET + 16 * 16)
+
+int g4r_context_fetch_matrix(G4RContext* ctx, const void* src, size_t row_stride, int world, cudaStream_t s) {
+    G4R_CUDA_OK(cudaMemcpy2DAsync(ctx->host_n + CTX_MATRIX_OFFSET, sizeof(int32_t) * world, src, row_stride, sizeof(int32_t) * world, world,
+                                  cudaMemcpyDeviceToHost, s));
+    G4R_CUDA_OK(cudaEventRecord(ctx->ev_matrix, s));
+    ctx->matrix_pending = true;
+    return G4R_OK;
+}
+int g4r_context_wait_matrix(G4RContext* ctx, int world, int32_t* out) {
+    if (!ctx->matrix_pending) return g4r_set_error(G4R_EINVAL, "no count matrix was requested");
+    G4R_CUDA_OK(cudaEventSynchronize(ctx->ev_matrix));
+    ctx->matrix_pending = false;
+    memcpy(out, ctx->host_n + CTX_MATRIX_OFFSET, sizeof(int32_t) * world * world);
+    return G4R_OK;
+}
 
 // Experiment switches: G4R_TUNE_<NAME> in the environment, read once per name.
 int g4r_tunable(const char* name, int dflt) {
@@ -130,9 +149,10 @@ int g4r_context_create(G4RContext** out) {
     if (!out) return g4r_set_error(G4R_EINVAL, "out is NULL");
     G4RContext* c = new (std::nothrow) G4RContext();
     if (!c) return g4r_set_error(G4R_EINVAL, "out of host memory");
-    c->host_n = nullptr; c->ev = nullptr; c->pending = false; c->renders_since_project = 0;
-    cudaError_t e = cudaMallocHost((void**)&c->host_n, sizeof(int32_t) * 4);
+    c->host_n = nullptr; c->ev = nullptr; c->ev_matrix = nullptr; c->pending = false; c->matrix_pending = false; c->renders_since_project = 0;
+    cudaError_t e = cudaMallocHost((void**)&c->host_n, sizeof(int32_t) * CTX_PINNED_INTS);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_matrix, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         if (c->host_n) cudaFreeHost(c->host_n);
         delete c;
@@ -146,6 +166,7 @@ int g4r_context_create(G4RContext** out) {
 void g4r_context_destroy(G4RContext* c) {
     if (!c) return;
     if (c->ev) cudaEventDestroy(c->ev);
+    if (c->ev_matrix) cudaEventDestroy(c->ev_matrix);
     if (c->host_n) cudaFreeHost(c->host_n);
     delete c;
 }

@@ -169,6 +169,9 @@ int launch_tile_rows(const G4RFrame& f, int P, const int32_t* radii, const void*
 int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
                         void* sort_scratch, int64_t capacity, bool record_overflow, cudaStream_t s);
 int g4r_overflow_read(int reset, unsigned int* out);
+// world x world int matrix, row r at src + r * row_stride: asynchronous copy into the context's pinned buffer + an event
+int g4r_context_fetch_matrix(G4RContext* ctx, const void* src, size_t row_stride, int world, cudaStream_t s);
+int g4r_context_wait_matrix(G4RContext* ctx, int world, int32_t* out);
 int launch_composite_forward(const G4RFrame& f, int P, const void* geom, void* img, const void* binning, int64_t capacity,
                              const G4RForwardOut& out, cudaStream_t s);
 int launch_composite_backward(const G4RFrame& f, int P, const void* geom, const void* img, const void* binning,

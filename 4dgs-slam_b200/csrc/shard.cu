@@ -154,9 +154,10 @@ __global__ void __launch_bounds__(G4R_BLOCK) shard_pack_kernel(int P, const int3
 // Receiver: radius of every slot of the received slabs (0 for the unused tail of each source's slab).
 // Slot j = s * (cap + 1) + k of the received slabs (row `cap` of every slab is its header and counts as unused).
 __global__ void __launch_bounds__(G4R_BLOCK) shard_unpack_kernel(uint32_t world, uint32_t cap, const float4* __restrict__ slab,
-                                                                 int32_t* __restrict__ radii_all) {
+                                                                 int32_t* __restrict__ radii_all, int32_t* __restrict__ n_touched_all) {
     const size_t j = (size_t)blockIdx.x * G4R_BLOCK + threadIdx.x;
     if (j >= (size_t)world * (cap + 1)) return;
+    if (n_touched_all) n_touched_all[j] = 0;                       // accumulated by composite_forward_kernel
     const uint32_t s = (uint32_t)(j / (cap + 1)), k = (uint32_t)(j % (cap + 1));
     const int32_t n = min(__float_as_int(__ldg(reinterpret_cast<const float*>(slab + ((size_t)s * (cap + 1) + cap) * 3))), (int32_t)cap);
     radii_all[j] = (int32_t)k < n ? __float_as_int(__ldg(reinterpret_cast<const float*>(slab + j * 3 + 2) + 3)) : 0;
@@ -194,20 +195,24 @@ __global__ void __launch_bounds__(G4R_BLOCK) shard_gather_int_kernel(int P, uint
     out[i] = v;
 }
 
-// All-gathered strips [world][planes][maxh][W] -> images [planes][H][W].
-__global__ void __launch_bounds__(G4R_BLOCK) shard_assemble_kernel(int W, int H, int planes, int maxh, size_t rank_stride, const ShardGeom g,
+// All-gathered strips (rank r: [planes][maxh][W] at strips + r * rank_stride) -> images [planes][H][W].
+// blockIdx.y = plane * H + y; threads cover the row in float4 steps when W % 4 == 0 and the bases are 16-byte aligned.
+template <bool kVec>
+__global__ void __launch_bounds__(G4R_BLOCK) shard_assemble_kernel(int W, int H, int maxh, size_t rank_stride, const ShardGeom g,
                                                                    const float* __restrict__ strips, float* __restrict__ images) {
-    const size_t idx = (size_t)blockIdx.x * G4R_BLOCK + threadIdx.x;
-    const size_t X = (size_t)W * H;
-    if (idx >= X * planes) return;
-    const int pl = (int)(idx / X);
-    const size_t pix = idx % X;
-    const int y = (int)(pix / W), x = (int)(pix % W);
+    const int pl = blockIdx.y / H, y = blockIdx.y % H;
     const uint32_t ty = (uint32_t)y / G4R_TILE;
     uint32_t r = 0;
     while (r + 1 < g.world && ty >= g.row_begin[r + 1]) ++r;
     const int yy = y - (int)g.row_begin[r] * G4R_TILE;
-    images[idx] = __ldg(strips + (size_t)r * rank_stride + ((size_t)pl * maxh + yy) * W + x);
+    const float* src = strips + (size_t)r * rank_stride + ((size_t)pl * maxh + yy) * W;
+    float* dst = images + ((size_t)pl * H + y) * W;
+    if (kVec) {
+        for (int x = blockIdx.x * G4R_BLOCK + threadIdx.x; x < W / 4; x += gridDim.x * G4R_BLOCK)
+            reinterpret_cast<float4*>(dst)[x] = __ldg(reinterpret_cast<const float4*>(src) + x);
+    } else {
+        for (int x = blockIdx.x * G4R_BLOCK + threadIdx.x; x < W; x += gridDim.x * G4R_BLOCK) dst[x] = __ldg(src + x);
+    }
 }
 
 static int check_world(const G4RFrame* f, int world) {
@@ -257,12 +262,12 @@ int g4r_shard_pack(const G4RFrame* f, int32_t P, const int32_t* radii, const voi
     return G4R_OK;
 }
 
-int g4r_shard_unpack(int32_t world, int64_t cap, const void* recv_slab, int32_t* radii_all, void* stream) {
+int g4r_shard_unpack(int32_t world, int64_t cap, const void* recv_slab, int32_t* radii_all, int32_t* n_touched_all, void* stream) {
     if (world < 1 || world > SHARD_MAX_WORLD || cap < 1) return g4r_set_error(G4R_EINVAL, "bad world / capacity");
     if (!recv_slab || !radii_all) return g4r_set_error(G4R_EINVAL, "NULL argument");
     const size_t n = (size_t)world * (size_t)(cap + 1);
     shard_unpack_kernel<<<(unsigned)((n + G4R_BLOCK - 1) / G4R_BLOCK), G4R_BLOCK, 0, (cudaStream_t)stream>>>(
-        (uint32_t)world, (uint32_t)cap, (const float4*)recv_slab, radii_all);
+        (uint32_t)world, (uint32_t)cap, (const float4*)recv_slab, radii_all, n_touched_all);
     G4R_LAUNCH_OK("shard_unpack_kernel");
     return G4R_OK;
 }
@@ -293,11 +298,23 @@ int g4r_shard_assemble(const G4RFrame* f, int32_t world, int32_t planes, int32_t
     if ((rc = check_world(f, world)) != G4R_OK) return rc;
     if (!strips || !images || planes < 1 || maxh < 1) return g4r_set_error(G4R_EINVAL, "bad strips / images / planes / maxh");
     const ShardGeom g = make_geom(*f, world, 1);
-    const size_t n = (size_t)f->width * f->height * planes;
-    shard_assemble_kernel<<<(unsigned)((n + G4R_BLOCK - 1) / G4R_BLOCK), G4R_BLOCK, 0, (cudaStream_t)stream>>>(f->width, f->height, planes, maxh,
-                                                                                                             (size_t)rank_stride, g, strips, images);
+    const bool vec = f->width % 4 == 0 && rank_stride % 4 == 0 && ((size_t)maxh * f->width) % 4 == 0 &&
+                     (((uintptr_t)strips | (uintptr_t)images) & 15u) == 0;
+    const dim3 grid((unsigned)((f->width / (vec ? 4 : 1) + G4R_BLOCK - 1) / G4R_BLOCK), (unsigned)(planes * f->height));
+    if (vec) shard_assemble_kernel<true><<<grid, G4R_BLOCK, 0, (cudaStream_t)stream>>>(f->width, f->height, maxh, (size_t)rank_stride, g, strips, images);
+    else shard_assemble_kernel<false><<<grid, G4R_BLOCK, 0, (cudaStream_t)stream>>>(f->width, f->height, maxh, (size_t)rank_stride, g, strips, images);
     G4R_LAUNCH_OK("shard_assemble_kernel");
     return G4R_OK;
+}
+
+int g4r_shard_fetch_counts(G4RContext* ctx, const void* gathered, int64_t rank_stride_bytes, int64_t offset_bytes, int32_t world, void* stream) {
+    if (!ctx || !gathered || world < 1 || world > SHARD_MAX_WORLD) return g4r_set_error(G4R_EINVAL, "bad arguments");
+    return g4r_context_fetch_matrix(ctx, (const char*)gathered + offset_bytes, (size_t)rank_stride_bytes, world, (cudaStream_t)stream);
+}
+
+int g4r_shard_wait_counts(G4RContext* ctx, int32_t world, int32_t* out) {
+    if (!ctx || !out || world < 1 || world > SHARD_MAX_WORLD) return g4r_set_error(G4R_EINVAL, "bad arguments");
+    return g4r_context_wait_matrix(ctx, world, out);
 }
 
 }  // extern "C"

@@ -90,7 +90,11 @@ _lib.g4r_shard_scratch_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
 _lib.g4r_shard_pack.restype = ctypes.c_int
 _lib.g4r_shard_pack.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64] + [ctypes.c_void_p] * 5
 _lib.g4r_shard_unpack.restype = ctypes.c_int
-_lib.g4r_shard_unpack.argtypes = [ctypes.c_int32, ctypes.c_int64] + [ctypes.c_void_p] * 3
+_lib.g4r_shard_unpack.argtypes = [ctypes.c_int32, ctypes.c_int64] + [ctypes.c_void_p] * 4
+_lib.g4r_shard_fetch_counts.restype = ctypes.c_int
+_lib.g4r_shard_fetch_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]
+_lib.g4r_shard_wait_counts.restype = ctypes.c_int
+_lib.g4r_shard_wait_counts.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
 _lib.g4r_shard_gather.restype = ctypes.c_int
 _lib.g4r_shard_gather.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
@@ -122,29 +126,31 @@ class CudaBackend:
             _check(_lib.g4r_project_only(ctypes.byref(fr["full"]), ctypes.byref(g), geom.data_ptr(), radii.data_ptr(), n_touched.data_ptr(),
                                          fr["stream"]))
 
-    def pack(self, fr, P, radii, geom, world, cap, send_slab, counts, slots):
+    def pack(self, fr, P, radii, geom, world, cap, send_slab, payload, counts_offset, slots):
+        """`counts` (this rank's row of the count matrix) is written into payload[counts_offset : counts_offset + world]."""
         scratch = torch.empty((_lib.g4r_shard_scratch_bytes(P, world),), dtype=torch.uint8, device=fr["dev"])
         with torch.cuda.device(fr["dev"]):
             _check(_lib.g4r_shard_pack(ctypes.byref(fr["full"]), P, radii.data_ptr(), geom.data_ptr(), world, cap, send_slab.data_ptr(),
-                                       counts.data_ptr(), slots.data_ptr(), scratch.data_ptr(), fr["stream"]))
+                                       payload.data_ptr() + 4 * counts_offset, slots.data_ptr(), scratch.data_ptr(), fr["stream"]))
 
-    def render_strip(self, fr, rows, world, cap, recv_slab, n_touched_all, strip, W, img_state, cap_hint):
-        """Unpack + bin + sort + composite of the strip `rows` = (begin, end) over the world*(cap+1) received slots; writes the
-        strip buffer [5, maxh, W].  Returns (binning, N)."""
+    def render_strip(self, fr, rows, world, cap, recv_slab, payload, strip_elems, maxh, W, img_state, cap_hint):
+        """Unpack + bin + sort + composite of the strip `rows` = (begin, end) over the world*(cap+1) received slots.  `payload` is
+        this rank's all-gather send buffer: the strip [5, maxh, W] at element 0, the n_touched slots behind it.  Returns (binning, N)."""
         dev = fr["dev"]
         P_all = world * (cap + 1)
-        maxh = int(strip.shape[1])
         radii_all = torch.empty((P_all,), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             ctx = _context(dev)
             stream = fr["stream"]
             frame = fr["strip"]
-            _check(_lib.g4r_shard_unpack(world, cap, recv_slab.data_ptr(), radii_all.data_ptr(), stream))
+            strip_ptr = payload.data_ptr()
+            nt_ptr = strip_ptr + 4 * strip_elems
+            _check(_lib.g4r_shard_unpack(world, cap, recv_slab.data_ptr(), radii_all.data_ptr(), nt_ptr, stream))
             g = _make_gaussians(P_all, recv_slab, recv_slab, None, None, None, None, None)
             _check(_lib.g4r_count_tiles(ctx, ctypes.byref(frame), P_all, radii_all.data_ptr(), recv_slab.data_ptr(), img_state.data_ptr(), stream))
-            base = strip.data_ptr() - 4 * (16 * int(rows[0])) * W              # pixel row y of the image = row y - 16*begin of the strip
+            base = strip_ptr - 4 * (16 * int(rows[0])) * W              # pixel row y of the image = row y - 16*begin of the strip
             plane = maxh * W
-            out = _ForwardOut(base, base + 4 * 3 * plane, base + 4 * 4 * plane, radii_all.data_ptr(), n_touched_all.data_ptr(), plane)
+            out = _ForwardOut(base, base + 4 * 3 * plane, base + 4 * 4 * plane, radii_all.data_ptr(), nt_ptr, plane)
             cap_n = cap_hint
             u8 = dict(dtype=torch.uint8, device=dev)
             binning = torch.empty((_lib.g4r_binning_bytes(cap_n),), **u8)
@@ -167,20 +173,18 @@ class CudaBackend:
             _check(_lib.g4r_shard_assemble(ctypes.byref(fr["full"]), world, PLANES, maxh, rank_stride, payload.data_ptr(), images.data_ptr(),
                                            fr["stream"]))
 
-    def host_copy(self, st, t: torch.Tensor):
-        """Start an asynchronous copy of a small device tensor to (cached) pinned host memory; returns a function that waits for
-        THAT copy only (an event recorded right behind it) and returns the host tensor -- the stream's later work keeps running."""
-        host = st.get("pinned")
-        if host is None or host.shape != t.shape:
-            host = st["pinned"] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            st["event"] = torch.cuda.Event()
-        host.copy_(t, non_blocking=True)
-        ev = st["event"]
-        ev.record(torch.cuda.current_stream(t.device))
+    def fetch_counts(self, fr, gathered, payload_elems, counts_offset, world):
+        """Start the asynchronous copy of the world x world count matrix (row r at gathered[r, counts_offset:]) into the native
+        context's pinned buffer; returns a function that waits for THAT copy only and returns the largest count."""
+        dev = fr["dev"]
+        with torch.cuda.device(dev):
+            ctx = _context(dev)
+            _check(_lib.g4r_shard_fetch_counts(ctx, gathered.data_ptr(), 4 * payload_elems, 4 * counts_offset, world, fr["stream"]))
 
         def wait():
-            ev.synchronize()
-            return host
+            buf = (ctypes.c_int32 * (world * world))()
+            _check(_lib.g4r_shard_wait_counts(ctx, world, buf))
+            return max(buf)
         return wait
 
     def gather(self, fr, P, world, cap, slots, acc_back=None, acc_stride=0, acc_local=None, nt_src=None, nt_offset=0, nt_stride=0, n_touched=None):
@@ -274,35 +278,32 @@ class _ShardedRasterize(torch.autograd.Function):
             slab_rows = cap + 1                                             # + the header row that carries the count
             # all-gather payload of this rank: [image strip | n_touched of the received records | its row of the count matrix]
             nt_elems = world * slab_rows
-            payload_elems = strip_elems + nt_elems + world
+            counts_offset = strip_elems + nt_elems
+            payload_elems = counts_offset + world
             payload = torch.empty((payload_elems,), **f32)
-            payload[strip_elems:strip_elems + nt_elems].zero_()
-            strip = payload[:strip_elems].view(PLANES, maxh, W)
-            ntouch_all = payload[strip_elems:strip_elems + nt_elems].view(torch.int32)
-            counts = payload[strip_elems + nt_elems:].view(torch.int32)
-            # 2. pack per destination (writes the slabs, their headers, `counts` and the slot table)
+            # 2. pack per destination (writes the slabs, their headers, this rank's counts and the slot table)
             send_slab = torch.empty((world, slab_rows, REC_FLOATS), **f32)
             slots = torch.empty((world, Pp), **i32)
-            backend.pack(fr, P, radii_local, geom_local, world, cap, send_slab, counts, slots)
+            backend.pack(fr, P, radii_local, geom_local, world, cap, send_slab, payload, counts_offset, slots)
             # 3. exchange the slabs
             recv_slab = torch.empty((world, slab_rows, REC_FLOATS), **f32)
             dist.all_to_all_single(recv_slab, send_slab, group=group)
             # 4. owned strip
             img_state = torch.empty((backend.image_state_bytes(W, H),), dtype=torch.uint8, device=dev)
             cap_n = int(st["n_hint"] * 1.25) + 4096 if st["n_hint"] > 0 else max(4096, 6 * cap)
-            binning, N = backend.render_strip(fr, (rb, re_), world, cap, recv_slab, ntouch_all, strip, W, img_state, cap_n)
+            binning, N = backend.render_strip(fr, (rb, re_), world, cap, recv_slab, payload, strip_elems, maxh, W, img_state, cap_n)
             st["n_hint"] = max(N, int(st["n_hint"] * 0.95))
             # 5. one all-gather: strips -> full image on every rank, n_touched -> owners, count matrix -> everybody's host
-            gathered = torch.empty((world, payload_elems), **f32)
-            dist.all_gather_into_tensor(gathered.view(-1), payload, group=group)
-            counts_on_host = backend.host_copy(st, gathered[:, strip_elems + nt_elems:].view(torch.int32))
+            gathered = torch.empty((world * payload_elems,), **f32)
+            dist.all_gather_into_tensor(gathered, payload, group=group)
+            max_count = backend.fetch_counts(fr, gathered, payload_elems, counts_offset, world)
             images = torch.empty((PLANES, H, W), **f32)
             backend.assemble(fr, world, maxh, gathered, payload_elems, images)
             if P > 0:
                 backend.gather(fr, P, world, cap, slots, nt_src=gathered, nt_offset=strip_elems + rank * slab_rows, nt_stride=payload_elems,
                                n_touched=ntouch_local)
             # everything is enqueued: now look at the count matrix (identical on all ranks -> identical decision)
-            worst = int(counts_on_host().max())
+            worst = int(max_count())
             st["pair_hint"] = max(worst, int(st["pair_hint"] * 0.95))
             st["cap"] = cap
             if worst <= cap:

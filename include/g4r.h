@@ -211,7 +211,13 @@ int g4r_shard_pack(const G4RFrame* frame, int32_t P, const int32_t* radii, const
                    void* send_slab, int32_t* counts, int32_t* slots, void* scratch, void* stream);
 /* Slabs are [world][cap + 1] records: row `cap` of slab d is its header {count, 0, ...}, so the counts travel inside the
  * all-to-all.  Received slots are numbered j = s * (cap + 1) + k; g4r_shard_unpack writes radii_all[world * (cap + 1)]. */
-int g4r_shard_unpack(int32_t world, int64_t cap, const void* recv_slab, int32_t* radii_all, void* stream);
+int g4r_shard_unpack(int32_t world, int64_t cap, const void* recv_slab, int32_t* radii_all, int32_t* n_touched_all /* zeroed; may be NULL */,
+                     void* stream);
+/* The world x world count matrix (row r = what rank r sent to everybody) sits at gathered + offset_bytes + r * rank_stride_bytes
+ * after the all-gather: g4r_shard_fetch_counts enqueues its copy into the context's pinned buffer plus an event,
+ * g4r_shard_wait_counts waits for THAT event only and copies the matrix out. */
+int g4r_shard_fetch_counts(G4RContext* ctx, const void* gathered, int64_t rank_stride_bytes, int64_t offset_bytes, int32_t world, void* stream);
+int g4r_shard_wait_counts(G4RContext* ctx, int32_t world, int32_t* out);
 /* acc_back / n_touched_back hold, for destination d, the rows that came back for the records this rank sent to d, starting at
  * row (element) d * stride: stride = cap + 1 rows after the reverse all-to-all, or the payload size when the data arrives
  * inside the strips' all-gather. */

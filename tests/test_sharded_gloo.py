@@ -99,13 +99,14 @@ class OracleBackend:
         rows = np.stack([np.where(vis, y0, 1), np.where(vis, y1 - 1, 0)], 1).astype(np.int32)
         return torch.from_numpy(rows)
 
-    def host_copy(self, st, t):
-        c = t.clone()
-        return lambda: c
+    def fetch_counts(self, fr, gathered, payload_elems, counts_offset, world):
+        m = int(gathered.view(world, payload_elems)[:, counts_offset:].contiguous().view(torch.int32).max())
+        return lambda: m
 
-    def pack(self, fr, P, radii, geom, world, cap, send_slab, counts, slots):
+    def pack(self, fr, P, radii, geom, world, cap, send_slab, payload, counts_offset, slots):
         from diff_gaussian_rasterization.sharded import strip_bounds
         rs = fr["rs"]
+        counts = payload[counts_offset:counts_offset + world].view(torch.int32)
         H = int(rs.image_height)
         ty = (H + 15) // 16
         slots.fill_(-1)
@@ -126,9 +127,12 @@ class OracleBackend:
             keep = idx[:cap]
             send_slab[d, :len(keep)] = rec[torch.from_numpy(keep)]
 
-    def render_strip(self, fr, rows, world, cap, recv_slab, n_touched_all, strip, W, img_state, cap_hint):
+    def render_strip(self, fr, rows, world, cap, recv_slab, payload, strip_elems, maxh, W, img_state, cap_hint):
         rs = fr["rs"]
         H = int(rs.image_height)
+        strip = payload[:strip_elems].view(5, maxh, W)
+        n_touched_all = payload[strip_elems:strip_elems + world * (cap + 1)].view(torch.int32)
+        n_touched_all.zero_()
         rec_all = recv_slab.reshape(world * (cap + 1), 12).clone()
         radii_all = rec_all[:, 11].contiguous().view(torch.int32).clone()
         for s_ in range(world):
