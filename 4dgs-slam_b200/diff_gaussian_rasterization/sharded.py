@@ -11,8 +11,8 @@ forward   1. project the local shard                                            
           4. bin / sort / composite the OWNED strip over the received records, straight into an all-gather send buffer
                                                                                   g4r_shard_unpack, g4r_count_tiles, g4r_forward_render
           5. ONE all-gather whose payload is [image strip | n_touched of the received records | row of the count matrix]
-             -> full image on every rank (g4r_shard_assemble), n_touched summed at the owners (g4r_shard_gather), and the
-             world x world count matrix on every rank's host
+             -> full image on every rank (g4r_shard_assemble), n_touched summed at the owners (g4r_shard_gather)
+          (a 4-byte all-reduce(max) of the pair counts sits in front of step 3: the overflow check of the slab capacity)
 backward  6. composite backward of the owned strip -> one accumulator row per received record   g4r_backward_composite
           7. reverse all-to-all of the rows; every owner sums the rows of its Gaussians         g4r_shard_gather
           8. per-Gaussian backward of the local shard; all-reduce of the 6 pose-gradient floats g4r_backward_gaussians
@@ -70,7 +70,7 @@ def collective_bytes(W: int, H: int, world: int, cap: int) -> dict:
     """Bytes every rank SENDS per frame in each collective (what bench.py reports next to the sharded timing)."""
     _, maxh = _strip_rows(H, world)
     rows = cap + 1
-    return {"all_to_all_records": world * rows * REC_FLOATS * 4,
+    return {"all_reduce_max_pair_count": 4, "all_to_all_records": world * rows * REC_FLOATS * 4,
             "all_gather_strip_ntouched_counts": (PLANES * maxh * W + world * rows + world) * 4,
             "all_to_all_accumulators": world * rows * ACC_FLOATS * 4, "all_reduce_pose_gradient": 32}
 
@@ -173,18 +173,18 @@ class CudaBackend:
             _check(_lib.g4r_shard_assemble(ctypes.byref(fr["full"]), world, PLANES, maxh, rank_stride, payload.data_ptr(), images.data_ptr(),
                                            fr["stream"]))
 
-    def fetch_counts(self, fr, gathered, payload_elems, counts_offset, world):
-        """Start the asynchronous copy of the world x world count matrix (row r at gathered[r, counts_offset:]) into the native
-        context's pinned buffer; returns a function that waits for THAT copy only and returns the largest count."""
+    def fetch_scalar(self, fr, t: torch.Tensor):
+        """Start the asynchronous copy of a 1-element int32 device tensor into the native context's pinned buffer; returns a
+        function that waits for THAT copy only (an event recorded right behind it) and returns the value."""
         dev = fr["dev"]
         with torch.cuda.device(dev):
             ctx = _context(dev)
-            _check(_lib.g4r_shard_fetch_counts(ctx, gathered.data_ptr(), 4 * payload_elems, 4 * counts_offset, world, fr["stream"]))
+            _check(_lib.g4r_shard_fetch_counts(ctx, t.data_ptr(), 4, 0, 1, fr["stream"]))
 
         def wait():
-            buf = (ctypes.c_int32 * (world * world))()
-            _check(_lib.g4r_shard_wait_counts(ctx, world, buf))
-            return max(buf)
+            buf = (ctypes.c_int32 * 1)()
+            _check(_lib.g4r_shard_wait_counts(ctx, 1, buf))
+            return int(buf[0])
         return wait
 
     def gather(self, fr, P, world, cap, slots, acc_back=None, acc_stride=0, acc_local=None, nt_src=None, nt_offset=0, nt_stride=0, n_touched=None):
@@ -279,12 +279,18 @@ class _ShardedRasterize(torch.autograd.Function):
             # all-gather payload of this rank: [image strip | n_touched of the received records | its row of the count matrix]
             nt_elems = world * slab_rows
             counts_offset = strip_elems + nt_elems
-            payload_elems = counts_offset + world
+            payload_elems = (counts_offset + world + 3) // 4 * 4            # 16-byte multiples keep the strip assembly vectorised
             payload = torch.empty((payload_elems,), **f32)
             # 2. pack per destination (writes the slabs, their headers, this rank's counts and the slot table)
             send_slab = torch.empty((world, slab_rows, REC_FLOATS), **f32)
             slots = torch.empty((world, Pp), **i32)
             backend.pack(fr, P, radii_local, geom_local, world, cap, send_slab, payload, counts_offset, slots)
+            # The largest count of any (source, destination) pair decides whether the slabs were big enough.  It is reduced
+            # right here -- a 4-byte all-reduce in front of the all-to-all -- so that the host can look at it at the end of
+            # forward without waiting for anything late in the stream (the composite is still running then).
+            worst_dev = payload[counts_offset:counts_offset + world].view(torch.int32).max().view(1)
+            dist.all_reduce(worst_dev, op=dist.ReduceOp.MAX, group=group)
+            max_count = backend.fetch_scalar(fr, worst_dev)
             # 3. exchange the slabs
             recv_slab = torch.empty((world, slab_rows, REC_FLOATS), **f32)
             dist.all_to_all_single(recv_slab, send_slab, group=group)
@@ -293,16 +299,15 @@ class _ShardedRasterize(torch.autograd.Function):
             cap_n = int(st["n_hint"] * 1.25) + 4096 if st["n_hint"] > 0 else max(4096, 6 * cap)
             binning, N = backend.render_strip(fr, (rb, re_), world, cap, recv_slab, payload, strip_elems, maxh, W, img_state, cap_n)
             st["n_hint"] = max(N, int(st["n_hint"] * 0.95))
-            # 5. one all-gather: strips -> full image on every rank, n_touched -> owners, count matrix -> everybody's host
+            # 5. one all-gather: strips -> full image on every rank, n_touched -> owners
             gathered = torch.empty((world * payload_elems,), **f32)
             dist.all_gather_into_tensor(gathered, payload, group=group)
-            max_count = backend.fetch_counts(fr, gathered, payload_elems, counts_offset, world)
             images = torch.empty((PLANES, H, W), **f32)
             backend.assemble(fr, world, maxh, gathered, payload_elems, images)
             if P > 0:
                 backend.gather(fr, P, world, cap, slots, nt_src=gathered, nt_offset=strip_elems + rank * slab_rows, nt_stride=payload_elems,
                                n_touched=ntouch_local)
-            # everything is enqueued: now look at the count matrix (identical on all ranks -> identical decision)
+            # everything is enqueued: now look at the largest pair count (identical on all ranks -> identical decision)
             worst = int(max_count())
             st["pair_hint"] = max(worst, int(st["pair_hint"] * 0.95))
             st["cap"] = cap

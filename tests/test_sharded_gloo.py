@@ -99,9 +99,9 @@ class OracleBackend:
         rows = np.stack([np.where(vis, y0, 1), np.where(vis, y1 - 1, 0)], 1).astype(np.int32)
         return torch.from_numpy(rows)
 
-    def fetch_counts(self, fr, gathered, payload_elems, counts_offset, world):
-        m = int(gathered.view(world, payload_elems)[:, counts_offset:].contiguous().view(torch.int32).max())
-        return lambda: m
+    def fetch_scalar(self, fr, t):
+        v = int(t[0])
+        return lambda: v
 
     def pack(self, fr, P, radii, geom, world, cap, send_slab, payload, counts_offset, slots):
         from diff_gaussian_rasterization.sharded import strip_bounds
