@@ -215,6 +215,13 @@ __global__ void __launch_bounds__(G4R_BLOCK) shard_assemble_kernel(int W, int H,
     }
 }
 
+__global__ void shard_max_count_kernel(const int32_t* __restrict__ counts, int world, int32_t* __restrict__ out) {
+    int32_t v = threadIdx.x < world ? counts[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) *out = v;
+}
+
 static int check_world(const G4RFrame* f, int world) {
     if (!f) return g4r_set_error(G4R_EINVAL, "frame is NULL");
     if (f->width <= 0 || f->height <= 0) return g4r_set_error(G4R_EINVAL, "image size %dx%d is not positive", f->width, f->height);
@@ -304,6 +311,13 @@ int g4r_shard_assemble(const G4RFrame* f, int32_t world, int32_t planes, int32_t
     if (vec) shard_assemble_kernel<true><<<grid, G4R_BLOCK, 0, (cudaStream_t)stream>>>(f->width, f->height, maxh, (size_t)rank_stride, g, strips, images);
     else shard_assemble_kernel<false><<<grid, G4R_BLOCK, 0, (cudaStream_t)stream>>>(f->width, f->height, maxh, (size_t)rank_stride, g, strips, images);
     G4R_LAUNCH_OK("shard_assemble_kernel");
+    return G4R_OK;
+}
+
+int g4r_shard_max_count(const int32_t* counts, int32_t world, int32_t* out, void* stream) {
+    if (!counts || !out || world < 1 || world > 32) return g4r_set_error(G4R_EINVAL, "bad arguments");
+    shard_max_count_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counts, world, out);
+    G4R_LAUNCH_OK("shard_max_count_kernel");
     return G4R_OK;
 }
 

@@ -33,6 +33,7 @@ library and there is no fallback.
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 
 import torch
@@ -372,17 +373,233 @@ class _ShardedRasterize(torch.autograd.Function):
                 None, None, None)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# native runtime (csrc/shard_nccl.cu): the frame's kernels AND collectives are enqueued by three C calls per forward and one per
+# backward.  Same algorithm, buffers and results as the Python-orchestrated path above; ~4x less host time per frame.
+# ----------------------------------------------------------------------------------------------------------------------
+class _ShardBuffers(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("cap", ctypes.c_int64), ("cap_n", ctypes.c_int64),
+                ("geom_local", ctypes.c_void_p), ("radii_local", ctypes.c_void_p), ("n_touched_local", ctypes.c_void_p),
+                ("send_slab", ctypes.c_void_p), ("recv_slab", ctypes.c_void_p), ("slots", ctypes.c_void_p), ("pack_scratch", ctypes.c_void_p),
+                ("payload", ctypes.c_void_p), ("strip_elems", ctypes.c_int64), ("maxh", ctypes.c_int64), ("counts_offset", ctypes.c_int64),
+                ("payload_elems", ctypes.c_int64), ("gathered", ctypes.c_void_p), ("images", ctypes.c_void_p), ("img_state", ctypes.c_void_p),
+                ("binning", ctypes.c_void_p), ("sort_scratch", ctypes.c_void_p), ("radii_all", ctypes.c_void_p), ("worst", ctypes.c_void_p)]
+
+
+_vp = ctypes.c_void_p
+_lib.g4r_shard_buffers_size.restype = ctypes.c_int
+_lib.g4r_shard_nccl_load.restype = ctypes.c_int
+_lib.g4r_shard_nccl_load.argtypes = [ctypes.c_char_p]
+_lib.g4r_shard_nccl_unique_id.restype = ctypes.c_int
+_lib.g4r_shard_nccl_unique_id.argtypes = [_vp]
+_lib.g4r_shard_comm_create.restype = ctypes.c_int
+_lib.g4r_shard_comm_create.argtypes = [_vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_vp)]
+_lib.g4r_shard_forward_a.restype = ctypes.c_int
+_lib.g4r_shard_forward_a.argtypes = [_vp] * 7
+_lib.g4r_shard_render_owned.restype = ctypes.c_int
+_lib.g4r_shard_render_owned.argtypes = [_vp] * 4
+_lib.g4r_shard_forward_wait.restype = ctypes.c_int
+_lib.g4r_shard_forward_wait.argtypes = [_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+_lib.g4r_shard_forward_b.restype = ctypes.c_int
+_lib.g4r_shard_forward_b.argtypes = [_vp, _vp, ctypes.c_int32, _vp, _vp]
+_lib.g4r_shard_backward.restype = ctypes.c_int
+_lib.g4r_shard_backward.argtypes = [_vp] * 11 + [ctypes.c_int32, _vp]
+if _lib.g4r_shard_buffers_size() != ctypes.sizeof(_ShardBuffers):
+    raise ImportError("diff_gaussian_rasterization.sharded: G4RShardBuffers layout mismatch between libg4r.so and the Python bindings")
+
+_comm_lock = threading.Lock()
+_comms: dict = {}
+
+
+def _nccl_path():
+    """The NCCL library this process already has loaded (torch's)."""
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libnccl" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    return None
+
+
+def native_comm(group, dev):
+    """This library's own NCCL communicator over the ranks of `group` (created once per (group, device); collective)."""
+    key = (id(group) if group is not None else 0, str(dev))
+    with _comm_lock:
+        h = _comms.get(key)
+    if h is not None:
+        return h
+    path = _nccl_path()
+    _check(_lib.g4r_shard_nccl_load(path.encode() if path else None))
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ident = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (ctypes.c_uint8 * 128)()
+        _check(_lib.g4r_shard_nccl_unique_id(buf))
+        ident = torch.tensor(list(buf), dtype=torch.uint8)
+    ident = ident.to(dev)
+    dist.broadcast(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = (ctypes.c_uint8 * 128)(*ident.cpu().tolist())
+    out = ctypes.c_void_p()
+    with torch.cuda.device(dev):
+        _check(_lib.g4r_shard_comm_create(raw, rank, world, ctypes.byref(out)))
+    with _comm_lock:
+        _comms[key] = out.value
+    return out.value
+
+
+class _ShardedRasterizeNative(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs, group):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = means3D.device
+        H, W = int(rs.image_height), int(rs.image_width)
+        tiles_y, maxh = _strip_rows(H, world)
+        if world > tiles_y:
+            raise ValueError(f"{world} ranks but only {tiles_y} tile rows: a rank would own an empty strip")
+        P = int(means3D.shape[0])
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        means3D = _dev_f32(means3D, dev)
+        opacities = _dev_f32(opacities, dev)
+        sh = _dev_f32(sh, dev) if sh.numel() else sh
+        colors_precomp = _dev_f32(colors_precomp, dev) if colors_precomp.numel() else colors_precomp
+        scales = _dev_f32(scales, dev) if scales.numel() else scales
+        rotations = _dev_f32(rotations, dev) if rotations.numel() else rotations
+        cov3Ds_precomp = _dev_f32(cov3Ds_precomp, dev) if cov3Ds_precomp.numel() else cov3Ds_precomp
+        M = int(sh.size(1)) if sh.numel() else 0
+        st = _state((str(dev), W, H, world))
+        comm = native_comm(group, dev)
+        if st["P"] != P or st["Pmax"] is None:
+            sizes = torch.tensor([P], dtype=torch.int64, device=dev)
+            all_sizes = torch.empty((world,), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+            st["Pmax"], st["P"] = max(1, int(all_sizes.max().item())), P
+        Pmax = st["Pmax"]
+        rb, re_ = strip_bounds(tiles_y, world, rank)
+        keep = []
+        with torch.cuda.device(dev):
+            nctx = _context(dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            full = _make_frame(rs, dev, M, keep)
+            strip = _make_frame(rs, dev, 0, keep)
+            strip.tile_rank, strip.tile_world, strip.tile_row_begin, strip.tile_row_end = 0, 1, rb, re_
+            g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+            Pp = max(P, 1)
+            geom_local = torch.empty((_lib.g4r_geom_bytes(Pp),), **u8)
+            local_i = torch.zeros((2, Pp), **i32) if P == 0 else torch.empty((2, Pp), **i32)        # radii | n_touched
+            pack_scratch = torch.empty((_lib.g4r_shard_scratch_bytes(Pp, world) + 64,), **u8)
+            images = torch.empty((PLANES, H, W), **f32)
+            img_state = torch.empty((_lib.g4r_image_bytes(W, H),), **u8)
+            strip_elems = PLANES * maxh * W
+            for _attempt in range(3):
+                cap = min(Pmax, int(st["pair_hint"] * 1.25) + 256) if st["pair_hint"] > 0 else Pmax
+                rows = cap + 1
+                counts_offset = strip_elems + world * rows
+                payload_elems = (counts_offset + world + 3) // 4 * 4
+                payload = torch.empty((payload_elems,), **f32)
+                slabs = torch.empty((2, world, rows, REC_FLOATS), **f32)                             # send | recv
+                slots = torch.empty((world, Pp), **i32)
+                gathered = torch.empty((world * payload_elems,), **f32)
+                cap_n = int(st["n_hint"] * 1.25) + 4096 if st["n_hint"] > 0 else max(4096, 6 * cap)
+                binning = torch.empty((_lib.g4r_binning_bytes(cap_n),), **u8)
+                sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap_n),), **u8)
+                all_i = torch.empty((world * rows + 4,), **i32)                                      # radii_all | worst
+                b = _ShardBuffers(world, rank, cap, cap_n, geom_local.data_ptr(), local_i.data_ptr(), local_i.data_ptr() + 4 * Pp,
+                                  slabs.data_ptr(), slabs.data_ptr() + 4 * world * rows * REC_FLOATS, slots.data_ptr(), pack_scratch.data_ptr(),
+                                  payload.data_ptr(), strip_elems, maxh, counts_offset, payload_elems, gathered.data_ptr(), images.data_ptr(),
+                                  img_state.data_ptr(), binning.data_ptr(), sort_scratch.data_ptr(), all_i.data_ptr(),
+                                  all_i.data_ptr() + 4 * world * rows)
+                _check(_lib.g4r_shard_forward_a(comm, nctx, ctypes.byref(full), ctypes.byref(strip), ctypes.byref(g), ctypes.byref(b), stream))
+                N, worst = ctypes.c_int64(), ctypes.c_int64()
+                _check(_lib.g4r_shard_forward_wait(nctx, ctypes.byref(N), ctypes.byref(worst)))
+                N, worst = int(N.value), int(worst.value)
+                st["pair_hint"] = max(worst, int(st["pair_hint"] * 0.95))
+                st["n_hint"] = max(N, int(st["n_hint"] * 0.95))
+                st["cap"] = cap
+                if worst > cap:
+                    st["redos"] += 1             # some pair's slab was too small: every rank sees the same `worst` and redoes part a
+                    continue
+                if N > cap_n:                    # local: only this rank's strip outgrew its instance buffers
+                    cap_n = N
+                    binning = torch.empty((_lib.g4r_binning_bytes(cap_n),), **u8)
+                    sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap_n),), **u8)
+                    b.cap_n, b.binning, b.sort_scratch = cap_n, binning.data_ptr(), sort_scratch.data_ptr()
+                    _check(_lib.g4r_shard_render_owned(nctx, ctypes.byref(strip), ctypes.byref(b), stream))
+                _check(_lib.g4r_shard_forward_b(comm, ctypes.byref(full), P, ctypes.byref(b), stream))
+                break
+            else:
+                raise RuntimeError("sharded render: slab capacity kept overflowing")
+        ctx.rs, ctx.group, ctx.P, ctx.M, ctx.world, ctx.rank, ctx.cap, ctx.cap_n = rs, group, P, M, world, rank, cap, cap_n
+        ctx.frames = (full, strip, keep)
+        ctx.opacities_shape = tuple(opacities.shape)
+        ctx.geo = (strip_elems, maxh, counts_offset, payload_elems)
+        ctx.save_for_backward(means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, local_i, geom_local, slabs, img_state, slots, binning)
+        radii = local_i[0, :P]
+        n_touched = local_i[1, :P]
+        ctx.mark_non_differentiable(radii, n_touched)
+        return images[0:3], radii, images[3:4], images[4:5], n_touched
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_opacity, grad_ntouched):
+        means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, local_i, geom_local, slabs, img_state, slots, binning = ctx.saved_tensors
+        group, P, M, world, rank, cap = ctx.group, ctx.P, ctx.M, ctx.world, ctx.rank, ctx.cap
+        full, strip, _keep = ctx.frames
+        dev = means3D.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        grad_color = _dev_f32(grad_color, dev)
+        grad_depth = _dev_f32(grad_depth, dev)
+        rows = cap + 1
+        Pp = max(P, 1)
+        acc = torch.empty((2 * world * rows + Pp, ACC_FLOATS), **f32)                                 # acc_all | acc_back | acc_local
+        grads = dict(means3D=torch.empty((P, 3), **f32), means2D=torch.empty((P, 3), **f32), opacities=torch.empty(ctx.opacities_shape, **f32))
+        if sh.numel():
+            grads["sh"] = torch.empty((P, M, 3), **f32)
+        if colors_precomp.numel():
+            grads["colors"] = torch.empty((P, 3), **f32)
+        if scales.numel():
+            grads["scales"] = torch.empty((P, 3), **f32)
+            grads["rots"] = torch.empty((P, 4), **f32)
+        if cov3Ds_precomp.numel():
+            grads["cov"] = torch.empty((P, 6), **f32)
+        tau = torch.empty((8,), **f32)
+        needs = ctx.needs_input_grad
+        with torch.cuda.device(dev):
+            comm = native_comm(group, dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            g = _make_gaussians(P, means3D, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+            b = _ShardBuffers(world, rank, cap, ctx.cap_n, geom_local.data_ptr(), local_i.data_ptr(), local_i.data_ptr() + 4 * Pp, None,
+                              slabs.data_ptr() + 4 * world * rows * REC_FLOATS, slots.data_ptr(), None, None, ctx.geo[0], ctx.geo[1], ctx.geo[2],
+                              ctx.geo[3], None, None, img_state.data_ptr(), binning.data_ptr(), None, None, None)
+            io = _BackwardIO(None, None, _ptr(grads["means3D"]), _ptr(grads["means2D"]), _ptr(grads["opacities"]), _ptr(grads.get("sh")),
+                             _ptr(grads.get("colors")), _ptr(grads.get("scales")), _ptr(grads.get("rots")), _ptr(grads.get("cov")), tau.data_ptr())
+            a0 = acc.data_ptr()
+            step = 4 * ACC_FLOATS * world * rows
+            _check(_lib.g4r_shard_backward(comm, ctypes.byref(full), ctypes.byref(strip), ctypes.byref(g), ctypes.byref(b), grad_color.data_ptr(),
+                                           grad_depth.data_ptr(), a0, a0 + step, a0 + 2 * step, ctypes.byref(io), 1 if (needs[8] or needs[9]) else 0,
+                                           stream))
+        return (grads["means3D"], grads["means2D"], grads.get("sh"), grads.get("colors"), grads["opacities"], grads.get("scales"),
+                grads.get("rots"), grads.get("cov"), tau[3:6].view(1, -1) if needs[8] else None, tau[:3].view(1, -1) if needs[9] else None,
+                None, None)
+
+
 class ShardedGaussianRasterizer(torch.nn.Module):
     """Same call signature as ``GaussianRasterizer`` but every argument is the LOCAL shard of the Gaussians; returns the
     full image on every rank and the local ``radii`` / ``n_touched``.  The image gradients handed to backward must be
     identical on all ranks (every rank evaluates the loss on the full image)."""
 
-    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "alltoall"):
+    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "alltoall", native: bool = True):
+        """`backend` = None: the CUDA library.  `native` (only without an injected backend): True = the frame is enqueued by the
+        native runtime of csrc/shard_nccl.cu (own NCCL communicator, 4 C calls per fwd+bwd); False = the same steps orchestrated
+        from Python through torch.distributed (the path the gloo tests exercise with a CPU backend)."""
         super().__init__()
         if exchange != "alltoall":
             raise ValueError("exchange must be 'alltoall' (the all-gather variant of round 1 moved world x more bytes and was removed)")
         self.raster_settings = raster_settings
         self.group = group
+        self.native = bool(native) and backend is None and os.environ.get("G4R_SHARD_NATIVE", "1") != "0"      # env: A/B switch
         self.backend = backend if backend is not None else CudaBackend()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
@@ -392,5 +609,8 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         e = lambda t: torch.Tensor([]) if t is None else t
+        if self.native:
+            return _ShardedRasterizeNative.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
+                                                 e(theta), e(rho), self.raster_settings, self.group)
         return _ShardedRasterize.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
                                        e(theta), e(rho), self.raster_settings, self.group, self.backend)

@@ -226,6 +226,55 @@ int g4r_shard_gather(int32_t P, int32_t world, int64_t cap, const int32_t* slots
 /* strips: for rank r, [planes][maxh][W] floats starting at strips + r * rank_stride. */
 int g4r_shard_assemble(const G4RFrame* frame, int32_t world, int32_t planes, int32_t maxh, int64_t rank_stride, const float* strips,
                        float* images, void* stream);
+int g4r_shard_max_count(const int32_t* counts, int32_t world, int32_t* out, void* stream);
+
+/* ---- native runtime of the sharded render: kernels AND collectives of a frame enqueued by a handful of C calls --------------
+ * NCCL is resolved at run time from the library the process already loaded (g4r_shard_nccl_load(path or NULL)); the communicator
+ * is this library's own: rank 0 calls g4r_shard_nccl_unique_id, the caller distributes the 128 bytes, every rank calls
+ * g4r_shard_comm_create (collective).  Per frame:
+ *   g4r_shard_forward_a     project, pack, all-reduce(max pair count), all-to-all of the slabs, unpack, bin, sort, composite the
+ *                           owned strip into payload[0 .. strip_elems)
+ *   g4r_shard_forward_wait  waits for two EARLY events: the largest pair count (> cap: every rank redoes part a with larger slabs)
+ *                           and N of the owned strip (> cap_n: this rank re-runs g4r_shard_render_owned with larger buffers)
+ *   g4r_shard_forward_b     all-gather of the payloads, image assembly, n_touched of the local shard
+ *   g4r_shard_backward      composite backward of the owned strip, reverse all-to-all of the accumulator rows, per-Gaussian sums,
+ *                           per-Gaussian backward, all-reduce of dL_dtau (when reduce_pose != 0) */
+typedef struct G4RShardComm G4RShardComm;
+typedef struct G4RShardBuffers {      /* DEVICE pointers, all owned by the caller */
+    int32_t world, rank;
+    int64_t cap;                      /* records per (source, destination) pair; slabs have cap + 1 rows (header row last) */
+    int64_t cap_n;                    /* instance capacity of binning / sort_scratch */
+    void*    geom_local;              /* g4r_geom_bytes(P) */
+    int32_t* radii_local;             /* [P] */
+    int32_t* n_touched_local;         /* [P] */
+    void*    send_slab;               /* [world][cap+1][12] floats */
+    void*    recv_slab;               /* [world][cap+1][12] floats; saved for backward */
+    int32_t* slots;                   /* [world][P]; saved for backward */
+    void*    pack_scratch;            /* g4r_shard_scratch_bytes(P, world) */
+    float*   payload;                 /* [payload_elems]: strip [5][maxh][W] | n_touched [world][cap+1] | counts [world] | pad */
+    int64_t  strip_elems, maxh, counts_offset, payload_elems;
+    float*   gathered;                /* [world][payload_elems] */
+    float*   images;                  /* [5][H][W] */
+    void*    img_state;               /* g4r_image_bytes; saved */
+    void*    binning;                 /* g4r_binning_bytes(cap_n); saved */
+    void*    sort_scratch;            /* g4r_sort_scratch_bytes(cap_n) */
+    int32_t* radii_all;               /* [world * (cap+1)] */
+    int32_t* worst;                   /* [1] */
+} G4RShardBuffers;
+int g4r_shard_buffers_size(void);                      /* sizeof(G4RShardBuffers): FFI self-check */
+int g4r_shard_nccl_load(const char* path);
+int g4r_shard_nccl_unique_id(uint8_t* out128);
+int g4r_shard_comm_create(const uint8_t* id128, int32_t rank, int32_t world, G4RShardComm** out);
+void g4r_shard_comm_destroy(G4RShardComm* comm);
+int g4r_shard_forward_a(G4RShardComm* comm, G4RContext* ctx, const G4RFrame* full, const G4RFrame* strip, const G4RGaussians* g,
+                        const G4RShardBuffers* b, void* stream);
+int g4r_shard_render_owned(G4RContext* ctx, const G4RFrame* strip, const G4RShardBuffers* b, void* stream);
+int g4r_shard_forward_wait(G4RContext* ctx, int64_t* N, int64_t* worst);
+int g4r_shard_forward_b(G4RShardComm* comm, const G4RFrame* full, int32_t P, const G4RShardBuffers* b, void* stream);
+int g4r_shard_backward(G4RShardComm* comm, const G4RFrame* full, const G4RFrame* strip, const G4RGaussians* g, const G4RShardBuffers* b,
+                       const float* dL_dcolor, const float* dL_ddepth, void* acc_all, void* acc_back, void* acc_local,
+                       const G4RBackwardIO* io, int32_t reduce_pose, void* stream);
+
 /* First / last tile row touched by each Gaussian (rows[2*i], rows[2*i+1]; 1,0 when invisible).  Same rectangle arithmetic as
  * the binning kernels (inspection / tests). */
 int g4r_tile_rows(const G4RFrame* frame, int32_t P, const int32_t* radii, const void* geom, int32_t* rows, void* stream);
