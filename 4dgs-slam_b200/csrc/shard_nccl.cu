@@ -10,7 +10,8 @@
 // Collectives of one frame (all on the caller's stream, in this order):
 //   forward_a : all-reduce(max) of the largest (source, destination) pair count        4 B      overflow check of the slabs
 //               all-to-all of the slabs = grouped ncclSend / ncclRecv                   world x (cap+1) x 48 B per rank
-//   forward_b : all-gather of [image strip | n_touched of received records | counts]    payload_elems x 4 B per rank
+//   forward_b : grouped send/recv: every plane of the strip into its place in every peer's image, the n_touched segments
+//               back to their owners                                                     (5 x strip + cap+1) x 4 B per peer
 //   backward  : all-to-all of the accumulator rows (reverse direction)                  world x (cap+1) x 48 B per rank
 //               all-reduce(sum) of the pose gradient                                    32 B
 #include "g4r_common.cuh"
@@ -168,18 +169,45 @@ int g4r_shard_forward_wait(G4RContext* ctx, int64_t* N, int64_t* worst) {
     return G4R_OK;
 }
 
-// ---- forward, part b: all-gather of the payloads -> assemble the image -> n_touched of the local shard ------------------
+// ---- forward, part b: every rank's strip straight into every rank's image, n_touched back to the owners ----------------
+// The strips have unequal heights (tiles_y is rarely a multiple of world), so instead of an all-gather of padded strips plus an
+// assembly pass, each plane of the strip is SENT to its final place in every peer's [5][H][W] image (one grouped
+// ncclSend / ncclRecv, 6 messages per peer: 5 planes + the n_touched segment); the own strip is copied locally.
 int g4r_shard_forward_b(G4RShardComm* c, const G4RFrame* full, int32_t P, const G4RShardBuffers* b, void* stream) {
     if (!c || !full || !b) return g4r_set_error(G4R_EINVAL, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    G4R_NCCL_OK(g_nccl.AllGather(b->payload, b->gathered, (size_t)b->payload_elems, ncclFloat, c->comm, s));
-    if ((rc = g4r_shard_assemble(full, c->world, 5, (int32_t)b->maxh, b->payload_elems, b->gathered, b->images, stream)) != G4R_OK) return rc;
-    if (P > 0) {
-        const int32_t* nt = (const int32_t*)(b->gathered + b->strip_elems + (int64_t)c->rank * (b->cap + 1));
-        if ((rc = g4r_shard_gather(P, c->world, b->cap, b->slots, nullptr, 0, nullptr, nt, b->payload_elems, b->n_touched_local, stream)) != G4R_OK)
-            return rc;
+    const int W = full->width, H = full->height;
+    const int gy = (H + G4R_TILE - 1) / G4R_TILE;
+    const size_t X = (size_t)W * H;
+    const int64_t rows = b->cap + 1;
+    auto y0_of = [&](int r) { return (int)(((int64_t)r * gy) / c->world) * G4R_TILE; };
+    auto y1_of = [&](int r) { const int y = (int)(((int64_t)(r + 1) * gy) / c->world) * G4R_TILE; return y < H ? y : H; };
+    const int my0 = y0_of(c->rank), my1 = y1_of(c->rank);
+    const size_t my_n = (size_t)(my1 - my0) * W;
+    int32_t* nt_gather = (int32_t*)b->gathered;                           // [world][rows]: n_touched segments that came back
+    const int32_t* nt_all = (const int32_t*)(b->payload + b->strip_elems);
+    G4R_NCCL_OK(g_nccl.GroupStart());
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        const int ry0 = y0_of(r), ry1 = y1_of(r);
+        const size_t r_n = (size_t)(ry1 - ry0) * W;
+        for (int pl = 0; pl < 5; ++pl) {
+            if (my_n) G4R_NCCL_OK(g_nccl.Send(b->payload + (size_t)pl * b->maxh * W, my_n, ncclFloat, r, c->comm, s));
+            if (r_n) G4R_NCCL_OK(g_nccl.Recv(b->images + (size_t)pl * X + (size_t)ry0 * W, r_n, ncclFloat, r, c->comm, s));
+        }
+        G4R_NCCL_OK(g_nccl.Send(nt_all + (size_t)r * rows, (size_t)rows, ncclInt32, r, c->comm, s));
+        G4R_NCCL_OK(g_nccl.Recv(nt_gather + (size_t)r * rows, (size_t)rows, ncclInt32, r, c->comm, s));
     }
+    G4R_NCCL_OK(g_nccl.GroupEnd());
+    // own strip and own n_touched segment: local copies
+    if (my_n)
+        G4R_CUDA_OK(cudaMemcpy2DAsync(b->images + (size_t)my0 * W, X * sizeof(float), b->payload, (size_t)b->maxh * W * sizeof(float),
+                                      my_n * sizeof(float), 5, cudaMemcpyDeviceToDevice, s));
+    G4R_CUDA_OK(cudaMemcpyAsync(nt_gather + (size_t)c->rank * rows, nt_all + (size_t)c->rank * rows, (size_t)rows * sizeof(int32_t),
+                                cudaMemcpyDeviceToDevice, s));
+    if (P > 0 && (rc = g4r_shard_gather(P, c->world, b->cap, b->slots, nullptr, 0, nullptr, nt_gather, rows, b->n_touched_local, stream)) != G4R_OK)
+        return rc;
     return G4R_OK;
 }
 

@@ -449,6 +449,19 @@ def native_comm(group, dev):
     return out.value
 
 
+def _sticky(st: dict, key: str, need: int, limit: int) -> int:
+    """Capacity with hysteresis: grows to 1.25 x need (rounded up to 4096) when the current one is too small and only shrinks when
+    the need falls below half of it.  Identical on all ranks for the pair capacity (every rank sees the same `need`).  Stable
+    sizes let the caching allocator hand back the same blocks every frame (a capacity that tracks the need closely changes
+    every frame and costs a cudaMalloc + implicit synchronisation each time)."""
+    cur = st.get(key) or 0
+    if cur < need + 256 or cur > 2 * (need + 256) + 8192:
+        cur = (int(need * 1.25) + 256 + 4095) // 4096 * 4096
+    cur = min(cur, limit) if limit >= need else cur
+    st[key] = cur
+    return cur
+
+
 class _ShardedRasterizeNative(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs, group):
@@ -495,15 +508,15 @@ class _ShardedRasterizeNative(torch.autograd.Function):
             img_state = torch.empty((_lib.g4r_image_bytes(W, H),), **u8)
             strip_elems = PLANES * maxh * W
             for _attempt in range(3):
-                cap = min(Pmax, int(st["pair_hint"] * 1.25) + 256) if st["pair_hint"] > 0 else Pmax
+                cap = _sticky(st, "cap_alloc", st["pair_hint"], Pmax) if st["pair_hint"] > 0 else Pmax
                 rows = cap + 1
                 counts_offset = strip_elems + world * rows
                 payload_elems = (counts_offset + world + 3) // 4 * 4
                 payload = torch.empty((payload_elems,), **f32)
                 slabs = torch.empty((2, world, rows, REC_FLOATS), **f32)                             # send | recv
                 slots = torch.empty((world, Pp), **i32)
-                gathered = torch.empty((world * payload_elems,), **f32)
-                cap_n = int(st["n_hint"] * 1.25) + 4096 if st["n_hint"] > 0 else max(4096, 6 * cap)
+                gathered = torch.empty((world * rows,), **f32)                                       # n_touched segments coming back
+                cap_n = _sticky(st, "cap_n_alloc", st["n_hint"], 1 << 40) if st["n_hint"] > 0 else max(4096, 6 * cap)
                 binning = torch.empty((_lib.g4r_binning_bytes(cap_n),), **u8)
                 sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap_n),), **u8)
                 all_i = torch.empty((world * rows + 4,), **i32)                                      # radii_all | worst

@@ -236,7 +236,8 @@ int g4r_shard_max_count(const int32_t* counts, int32_t world, int32_t* out, void
  *                           owned strip into payload[0 .. strip_elems)
  *   g4r_shard_forward_wait  waits for two EARLY events: the largest pair count (> cap: every rank redoes part a with larger slabs)
  *                           and N of the owned strip (> cap_n: this rank re-runs g4r_shard_render_owned with larger buffers)
- *   g4r_shard_forward_b     all-gather of the payloads, image assembly, n_touched of the local shard
+ *   g4r_shard_forward_b     every plane of the strip sent to its place in every peer's image (grouped send/recv, no padding and no
+ *                           assembly pass), n_touched segments back to their owners and summed per Gaussian
  *   g4r_shard_backward      composite backward of the owned strip, reverse all-to-all of the accumulator rows, per-Gaussian sums,
  *                           per-Gaussian backward, all-reduce of dL_dtau (when reduce_pose != 0) */
 typedef struct G4RShardComm G4RShardComm;
@@ -253,7 +254,7 @@ typedef struct G4RShardBuffers {      /* DEVICE pointers, all owned by the calle
     void*    pack_scratch;            /* g4r_shard_scratch_bytes(P, world) */
     float*   payload;                 /* [payload_elems]: strip [5][maxh][W] | n_touched [world][cap+1] | counts [world] | pad */
     int64_t  strip_elems, maxh, counts_offset, payload_elems;
-    float*   gathered;                /* [world][payload_elems] */
+    float*   gathered;                /* native runtime: [world][cap+1] int32 n_touched segments; Python-orchestrated path: [world][payload_elems] */
     float*   images;                  /* [5][H][W] */
     void*    img_state;               /* g4r_image_bytes; saved */
     void*    binning;                 /* g4r_binning_bytes(cap_n); saved */
