@@ -102,6 +102,13 @@ int g4r_tunable(const char* name, int dflt) {
     return val;
 }
 
+// Sorted splat stream + TMA staging in the composite kernels (csrc/composite.cu): on / off for the whole process, because the
+// saved `binning` buffer has to have the same layout in forward and backward.
+bool g4r_stream_mode() {
+    static const bool on = g4r_tunable("STREAM", 0) != 0;
+    return on;
+}
+
 static int check_frame(const G4RFrame* f, bool backward) {
     if (!f) return g4r_set_error(G4R_EINVAL, "frame is NULL");
     if (f->width <= 0 || f->height <= 0) return g4r_set_error(G4R_EINVAL, "image size %dx%d is not positive", f->width, f->height);
@@ -173,7 +180,7 @@ void g4r_context_destroy(G4RContext* c) {
 
 size_t g4r_geom_bytes(int32_t P) { return GeomLayout(P < 0 ? 0 : P).total; }
 size_t g4r_image_bytes(int32_t W, int32_t H) { return ImageLayout(W < 1 ? 1 : W, H < 1 ? 1 : H).total; }
-size_t g4r_binning_bytes(int64_t capacity) { return BinLayout(capacity).total; }
+size_t g4r_binning_bytes(int64_t capacity) { return BinLayout(capacity, g4r_stream_mode()).total; }
 size_t g4r_sort_scratch_bytes(int64_t capacity) { return SortLayout(capacity).total; }
 size_t g4r_backward_scratch_bytes(int32_t P) { return g4r_align((size_t)(P < 1 ? 1 : P) * G4R_ACC_STRIDE * sizeof(float)) + 256; }
 
@@ -181,7 +188,7 @@ int g4r_layout(int32_t P, int32_t W, int32_t H, int64_t capacity, G4RLayout* out
     if (!out) return g4r_set_error(G4R_EINVAL, "out is NULL");
     const GeomLayout gl(P < 0 ? 0 : P);
     const ImageLayout il(W < 1 ? 1 : W, H < 1 ? 1 : H);
-    const BinLayout bl(capacity);
+    const BinLayout bl(capacity, g4r_stream_mode());
     out->geom_rec = gl.rec; out->geom_clamped = gl.clamped;
     out->img_final_T = il.final_T; out->img_n_contrib = il.n_contrib; out->img_ranges = il.ranges;
     out->img_counts = il.counts; out->img_header = il.header;

@@ -215,7 +215,26 @@ int launch_tile_rows(const G4RFrame& f, int P, const int32_t* radii, const void*
 #define BUCKET_MAX_FILL 24                      // a fuller bucket sends the tile to the bitonic path
 
 // Stable LSD radix pass over one tile segment living in global memory (rare, oversized tiles).
-static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, uint32_t* __restrict__ out_ids, uint32_t* s_hist, uint32_t* s_base) {
+// Sorted entry e of a tile: the id into point_list and, in stream mode, the Gaussian's 48-byte record (id in the spare slot)
+// into the sorted splat stream.
+struct SortOut {
+    uint32_t* point_list;
+    float4* stream;            // NULL: no stream
+    const float4* rec;
+    __device__ __forceinline__ void emit(uint32_t pos, uint32_t id) const {
+        point_list[pos] = id;
+        if (stream) {
+            const float4* r = rec + (size_t)id * 3;
+            const float4 a = ldg4(r), b = ldg4(r + 1);
+            float4 c = ldg4(r + 2);
+            c.w = __uint_as_float(id);
+            float4* d = stream + (size_t)pos * 3;
+            d[0] = a; d[1] = b; d[2] = c;
+        }
+    }
+};
+
+static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, const SortOut& out, uint32_t pos0, uint32_t* s_hist, uint32_t* s_base) {
     __shared__ int s_skip;
     __shared__ uint32_t s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,7 +297,7 @@ static __device__ void big_tile_sort(uint2* a, uint2* b, uint32_t L, uint32_t* _
         uint2* t = src; src = dst; dst = t;
         __syncthreads();
     }
-    for (uint32_t e = tid; e < L; e += G4R_BLOCK) out_ids[e] = src[e].y;
+    for (uint32_t e = tid; e < L; e += G4R_BLOCK) out.emit(pos0 + e, src[e].y);
 }
 
 // Bitonic network over n = 2^m >= L keys in shared memory (keys beyond L are +inf padding).
@@ -304,7 +323,7 @@ static __device__ void bitonic_sort(unsigned long long* s_key, uint32_t n) {
 // network over the next power of two.  Skewed tiles (a bucket fuller than BUCKET_MAX_FILL) and 2048 < L <= 4096 use the
 // bitonic network; larger tiles the CTA-local radix sort in global memory.  All three produce the same total order.
 __global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __restrict__ ranges, uint2* __restrict__ pairs,
-                                                              uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list,
+                                                              uint2* __restrict__ pairs_alt, const SortOut out,
                                                               const uint32_t* __restrict__ header, uint32_t capacity,
                                                               const uint32_t* __restrict__ order) {
     if (header[0] > capacity) return;
@@ -315,8 +334,8 @@ __global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __res
     const uint32_t L = range.y - range.x;
     if (L == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (L == 1) { if (tid == 0) point_list[range.x] = pairs[range.x].y; return; }
-    if (L > SORT_SMEM_MAX) { big_tile_sort(pairs + range.x, pairs_alt + range.x, L, point_list + range.x, s_cnt, s_cnt + 256); return; }
+    if (L == 1) { if (tid == 0) out.emit(range.x, pairs[range.x].y); return; }
+    if (L > SORT_SMEM_MAX) { big_tile_sort(pairs + range.x, pairs_alt + range.x, L, out, range.x, s_cnt, s_cnt + 256); return; }
 
     bool use_bitonic = L > BUCKET_MAX_L;
     if (!use_bitonic) {
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __res
                 }
             }
             __syncthreads();
-            for (uint32_t e = tid; e < L; e += G4R_BLOCK) point_list[range.x + e] = (uint32_t)s_out[e];
+            for (uint32_t e = tid; e < L; e += G4R_BLOCK) out.emit(range.x + e, (uint32_t)s_out[e]);
             return;
         }
 #undef BUCKET_OF
@@ -415,14 +434,14 @@ __global__ void __launch_bounds__(G4R_BLOCK) tile_sort_kernel(const uint2* __res
     }
     __syncthreads();
     bitonic_sort(s_key, n);
-    for (uint32_t e = tid; e < L; e += G4R_BLOCK) point_list[range.x + e] = (uint32_t)s_key[e];
+    for (uint32_t e = tid; e < L; e += G4R_BLOCK) out.emit(range.x + e, (uint32_t)s_key[e]);
 }
 
 int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,
                         void* sort_scratch, int64_t capacity, bool record_overflow, cudaStream_t s) {
     const GeomLayout gl(P);
     const ImageLayout il(f.width, f.height);
-    const BinLayout bl(capacity);
+    const BinLayout bl(capacity, g4r_stream_mode());
     const SortLayout sl(capacity);
     char* ib = (char*)img;
     char* bb = (char*)binning;
@@ -437,9 +456,13 @@ int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const vo
     g4r_stage_end(ST_SCATTER, s);
     G4R_LAUNCH_OK("scatter_kernel");
     static const bool lpt = g4r_tunable("LPT", 1) != 0;
+    SortOut sort_out;
+    sort_out.point_list = (uint32_t*)(bb + bl.point_list);
+    sort_out.stream = g4r_stream_mode() ? (float4*)(bb + bl.stream) : nullptr;
+    sort_out.rec = rec;
     g4r_stage_begin(ST_TILE_SORT, s);
     tile_sort_kernel<<<il.tiles, G4R_BLOCK, 0, s>>>((const uint2*)(ib + il.ranges), (uint2*)(sb + sl.pairs), (uint2*)(sb + sl.pairs_alt),
-                                                    (uint32_t*)(bb + bl.point_list), (const uint32_t*)(ib + il.header), cap,
+                                                    sort_out, (const uint32_t*)(ib + il.header), cap,
                                                     lpt ? (const uint32_t*)(ib + il.order) : nullptr);
     g4r_stage_end(ST_TILE_SORT, s);
     G4R_LAUNCH_OK("tile_sort_kernel");

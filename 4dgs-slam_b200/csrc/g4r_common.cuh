@@ -60,15 +60,21 @@ struct ImageLayout {     // per-pixel + per-tile state, saved for backward
         total = o + 256;
     }
 };
-struct BinLayout {       // per-instance state SAVED for backward (the reference's binningBuffer): the sorted id list
-    size_t point_list, total;
-    __host__ __device__ explicit BinLayout(int64_t cap) {
+// Per-instance state SAVED for backward (the reference's binningBuffer): the sorted id list and, in stream mode
+// (g4r_stream_mode()), the sorted splat STREAM -- the 48-byte records of every tile's list laid out contiguously in list
+// order (id in the spare slot), which is what lets the composite kernels stage a whole span with one TMA bulk copy.
+struct BinLayout {
+    size_t point_list, stream, total;
+    __host__ __device__ BinLayout(int64_t cap, bool with_stream) {
         size_t c = (size_t)(cap < 1 ? 1 : cap);
+        // whichever array the BACKWARD reads sits at offset 0, so that g4r_backward needs no capacity argument
         size_t o = 0;
+        stream = o;     o = g4r_align(o + (with_stream ? c * 48 : 0));
         point_list = o; o = g4r_align(o + c * 4);
         total = o + 256;
     }
 };
+bool g4r_stream_mode();      // process-wide: G4R_TUNE_STREAM (api.cu)
 struct SortLayout {      // per-instance scratch of the forward only (dies with the call): unsorted (depth bits, id) pairs
     size_t pairs, pairs_alt, total;
     __host__ __device__ explicit SortLayout(int64_t cap) {

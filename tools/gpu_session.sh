@@ -11,6 +11,7 @@ for stage in "$@"; do
     small)    timeout 600 python tools/gpu_check.py --golden > gpurun_out/check_small.log 2>&1; echo "rc=$?" ;;
     big)      timeout 900 python tools/gpu_check.py --big > gpurun_out/check_big.log 2>&1; echo "rc=$?" ;;
     pytest)   timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" ;;
+    pyteststream) G4R_TUNE_STREAM=1 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu_stream.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_gpu_stream.log ;;
     pytestall) timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" ;;
     smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "rc=$?" ;;
     memcheck) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/memcheck.log 2>&1; echo "rc=$?" ;;

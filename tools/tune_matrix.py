@@ -15,8 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
 
 VARIANTS = {
     "default": {},
-    "round-1 backward kernel (BWD_LEGACY=1)": {"BWD_LEGACY": 1},
-    "forward one splat per trip (FWD_PAIR=0)": {"FWD_PAIR": 0},
+    "sorted splat stream + TMA bulk staging (STREAM=1)": {"STREAM": 1},
 }
 if os.environ.get("G4R_VARIANTS"):          # e.g. G4R_VARIANTS='{"x": {"LPT": 0}}'
     VARIANTS = {"default": {}, **json.loads(os.environ["G4R_VARIANTS"])}
@@ -41,6 +40,7 @@ def scenes():
         "clustered200k": clustered(200_000, 640, 480, 4),
         "bigsplats100k": make_scene(100_000, 640, 480, sh_degree=0, seed=3, px_min=3.0, px_max=25.0),
         "C2": config_scene("C2"),
+        "C4": config_scene("C4"),
     }
 
 
