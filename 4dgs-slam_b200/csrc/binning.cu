@@ -156,6 +156,10 @@ __global__ void __launch_bounds__(G4R_BLOCK) scatter_kernel(int P, const int32_t
         }
 }
 
+// (Measured and removed again in round 2: a chunked variant in which a CTA histograms 2048 Gaussians per tile in shared memory
+// and touches each global counter once per (CTA, non-empty tile) -- 4.5x fewer global atomics.  Scatter 31.6 vs 32.3 us at C3,
+// 132 vs 87 us at C4 (profiles/r02_v4_tune_binning_chunked.json): same-address atomics are not what bounds this kernel.)
+
 // Sharded render: per-owned-tile histogram over the all-gathered records (project_kernel's fused histogram only sees
 // the local shard).
 __global__ void __launch_bounds__(G4R_BLOCK) count_tiles_kernel(int P, const int32_t* __restrict__ radii, const float4* __restrict__ rec,

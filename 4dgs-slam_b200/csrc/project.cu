@@ -67,11 +67,25 @@ template <bool kVec, bool kRaw = false>
 __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams p) {
     __shared__ __align__(16) float s_mean[G4R_BLOCK * 3];
     __shared__ __align__(16) float s_aux[G4R_BLOCK * 3];   // scales
+    __shared__ float s_cam[32];                            // view matrix [0,16), full projection [16,32): broadcast reads
     const int row0 = blockIdx.x * G4R_BLOCK;
     const int i = row0 + threadIdx.x;
     const bool has_scale = p.cov3D_precomp == nullptr;
 
     const bool iso = kRaw && p.scale_dim == 1;
+    if (threadIdx.x < 32) s_cam[threadIdx.x] = __ldg((threadIdx.x < 16 ? p.viewmatrix : p.projmatrix - 16) + threadIdx.x);
+    // The per-Gaussian loads that the arithmetic only needs late (rotation, opacity) are issued here, together with the staging
+    // loads, so that their latency overlaps instead of adding up behind the cull branches (ncu: 45 % of the stall samples of
+    // the round-1 kernel were long-scoreboard waits on loads issued one after the other).
+    float4 q_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+    float o_pre = 0.0f;
+    if (i < p.P) {
+        if (has_scale) {
+            if (kVec) q_pre = __ldg(reinterpret_cast<const float4*>(p.rotations) + i);
+            else { const float* q = p.rotations + (size_t)i * 4; q_pre = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3)); }
+        }
+        o_pre = __ldg(p.opacities + i);
+    }
     stage_rows3<kVec>(s_mean, p.means3D, row0, p.P);
     if (has_scale && !iso) stage_rows3<kVec>(s_aux, p.scales, row0, p.P);
     __syncthreads();
@@ -79,11 +93,10 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     p.n_touched[i] = 0;                          // accumulated by composite_forward_kernel
 
     const float x = s_mean[threadIdx.x * 3 + 0], y = s_mean[threadIdx.x * 3 + 1], z = s_mean[threadIdx.x * 3 + 2];
-    const float* __restrict__ V = p.viewmatrix;
-    const float* __restrict__ Q = p.projmatrix;
+    const float* __restrict__ Q = s_cam + 16;
     float v[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = __ldg(V + k);
+    for (int k = 0; k < 16; ++k) v[k] = s_cam[k];
 
     int radius_i = 0;
     // ---- near cull: p_view.z <= 0.2 (auxiliary.h:152-162) -----------------------------------
@@ -91,9 +104,9 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     if (depth <= 0.2f) { p.radii[i] = 0; return; }
 
     // ---- homogeneous projection (forward.cu:199-202) -------------------------------------------
-    const float hx_ = affine_row(__ldg(Q + 0), __ldg(Q + 4), __ldg(Q + 8), __ldg(Q + 12), x, y, z);
-    const float hy_ = affine_row(__ldg(Q + 1), __ldg(Q + 5), __ldg(Q + 9), __ldg(Q + 13), x, y, z);
-    const float hw_ = affine_row(__ldg(Q + 3), __ldg(Q + 7), __ldg(Q + 11), __ldg(Q + 15), x, y, z);
+    const float hx_ = affine_row(Q[0], Q[4], Q[8], Q[12], x, y, z);
+    const float hy_ = affine_row(Q[1], Q[5], Q[9], Q[13], x, y, z);
+    const float hw_ = affine_row(Q[3], Q[7], Q[11], Q[15], x, y, z);
     const float pw = __frcp_rn(__fadd_rn(hw_, 0.0000001f));
     const float ndc_x = __fmul_rn(hx_, pw);
     const float ndc_y = __fmul_rn(hy_, pw);
@@ -108,14 +121,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
         const float sx = __fmul_rn(p.scale_modifier, s0);
         const float sy = __fmul_rn(p.scale_modifier, s1);
         const float sz = __fmul_rn(p.scale_modifier, s2);
-        float qr, qx, qy, qz;                        // (r,x,y,z), NOT normalised (forward.cu:129)
-        if (kVec) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + i);
-            qr = q.x; qx = q.y; qy = q.z; qz = q.w;
-        } else {
-            const float* q = p.rotations + (size_t)i * 4;
-            qr = __ldg(q + 0); qx = __ldg(q + 1); qy = __ldg(q + 2); qz = __ldg(q + 3);
-        }
+        float qr = q_pre.x, qx = q_pre.y, qy = q_pre.z, qz = q_pre.w;     // (r,x,y,z), NOT normalised (forward.cu:129)
         if (kRaw) {                                  // rotation_activation = normalize
             const float n = g4r_quat_norm(qr, qx, qy, qz);
             qr = __fdiv_rn(qr, n); qx = __fdiv_rn(qx, n); qy = __fdiv_rn(qy, n); qz = __fdiv_rn(qz, n);
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     // The composite kernels minimise q over a warp's 8x4 pixel patch and skip the splat when the minimum exceeds
     // cull_q; the small padding absorbs float rounding of the per-pixel evaluation, so a skipped (warp, splat)
     // pair is always one the reference would have evaluated to alpha < 1/255 for all 32 pixels.
-    const float o = kRaw ? g4r_sigmoid(__ldg(p.opacities + i)) : __ldg(p.opacities + i);   // opacity_activation = sigmoid
+    const float o = kRaw ? g4r_sigmoid(o_pre) : o_pre;                                     // opacity_activation = sigmoid
     float cull_q = CUDART_INF_F;                    // no culling (degenerate conic / NaN)
     if (o < (1.0f / 255.0f)) {
         cull_q = -1.0f;                             // alpha = o*exp(power<=0) < 1/255 everywhere
