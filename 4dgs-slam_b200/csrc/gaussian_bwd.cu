@@ -21,6 +21,9 @@ struct GaussBwdParams {
     float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
     const float *means3D, *shs, *shs_rest, *colors_precomp, *scales, *rotations, *cov3D_precomp;
     int scale_dim;                // raw mode: 1 = isotropic _scaling [P,1]
+    const int32_t* dyn_slot;      // dynamic offsets (include/g4r.h); NULL on the reference surface
+    const float *dx, *ds, *dr;
+    float *dL_ddx, *dL_dds, *dL_ddr;
     const float *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
     const int32_t* radii;
     const float4* rec;
@@ -71,8 +74,18 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
         if (p.dL_dcov3D) { float* d = p.dL_dcov3D + (size_t)i * 6; for (int k = 0; k < 6; ++k) d[k] = 0.f; }
     }
 
+    const int slot = (in_range && p.dyn_slot != nullptr) ? p.dyn_slot[i] : -1;
+    if (in_range && !visible && slot >= 0) {     // a dynamic Gaussian that was culled / masked: its offset rows get zeros
+        if (p.dL_ddx) { float* d = p.dL_ddx + (size_t)slot * 3; d[0] = 0.f; d[1] = 0.f; d[2] = 0.f; }
+        if (p.dL_dds) { float* d = p.dL_dds + (size_t)slot * 3; d[0] = 0.f; d[1] = 0.f; d[2] = 0.f; }
+        if (p.dL_ddr) reinterpret_cast<float4*>(p.dL_ddr)[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
     if (visible) {
-        const float mx = __ldg(p.means3D + (size_t)i * 3), my = __ldg(p.means3D + (size_t)i * 3 + 1), mz = __ldg(p.means3D + (size_t)i * 3 + 2);
+        float mx = __ldg(p.means3D + (size_t)i * 3), my = __ldg(p.means3D + (size_t)i * 3 + 1), mz = __ldg(p.means3D + (size_t)i * 3 + 2);
+        if (slot >= 0 && p.dx != nullptr) {
+            mx += __ldg(p.dx + (size_t)slot * 3); my += __ldg(p.dx + (size_t)slot * 3 + 1); mz += __ldg(p.dx + (size_t)slot * 3 + 2);
+        }
 
         // accumulated screen-space gradients from composite_backward_kernel
         const float4* arow = reinterpret_cast<const float4*>(p.acc + (size_t)i * G4R_ACC_STRIDE);
@@ -87,6 +100,7 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
         const bool has_scale = p.cov3D_precomp == nullptr;
         float c0, c1, c2, c3, c4, c5;
         float sx = 0.f, sy = 0.f, sz = 0.f, qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        float nr = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;    // the normalised quaternion before the dynamic offset (raw mode chain rule)
         float act_s[3] = {0.f, 0.f, 0.f}, qnorm = 1.f;   // raw mode: activated scales (before the modifier), |_rotation|
         float R[3][3];   // R[a][k] = reference's glm R[col a][row k]; M[a][k] = s_k * R[a][k]
         if (has_scale) {
@@ -95,6 +109,9 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
             float s1 = iso ? s0 : __ldg(p.scales + (size_t)i * 3 + 1);
             float s2 = iso ? s0 : __ldg(p.scales + (size_t)i * 3 + 2);
             if (kRaw) { s0 = expf(s0); s1 = iso ? s0 : expf(s1); s2 = iso ? s0 : expf(s2); act_s[0] = s0; act_s[1] = s1; act_s[2] = s2; }
+            if (slot >= 0 && p.ds != nullptr) {
+                s0 += __ldg(p.ds + (size_t)slot * 3); s1 += __ldg(p.ds + (size_t)slot * 3 + 1); s2 += __ldg(p.ds + (size_t)slot * 3 + 2);
+            }
             sx = p.scale_modifier * s0;
             sy = p.scale_modifier * s1;
             sz = p.scale_modifier * s2;
@@ -103,6 +120,11 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
             if (kRaw) {
                 qnorm = g4r_quat_norm(qr, qx, qy, qz);
                 qr = __fdiv_rn(qr, qnorm); qx = __fdiv_rn(qx, qnorm); qy = __fdiv_rn(qy, qnorm); qz = __fdiv_rn(qz, qnorm);
+            }
+            nr = qr; nx = qx; ny = qy; nz = qz;
+            if (slot >= 0 && p.dr != nullptr) {
+                qr += __ldg(p.dr + (size_t)slot * 4); qx += __ldg(p.dr + (size_t)slot * 4 + 1);
+                qy += __ldg(p.dr + (size_t)slot * 4 + 2); qz += __ldg(p.dr + (size_t)slot * 4 + 3);
             }
             R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
             R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
@@ -296,11 +318,13 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) N[a][k] = 2.f * sk[k] * (dS[a][0] * R[0][k] + dS[a][1] * R[1][k] + dS[a][2] * R[2][k]);
-            if (p.dL_dscales) {
+            if (p.dL_dscales || (slot >= 0 && p.dL_dds)) {
                 float ds[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) ds[k] = R[0][k] * N[0][k] + R[1][k] * N[1][k] + R[2][k] * N[2][k];
-                if (kRaw) {                                                   // d exp(x) = exp(x) dx
+                if (slot >= 0 && p.dL_dds) { float* d = p.dL_dds + (size_t)slot * 3; d[0] = ds[0]; d[1] = ds[1]; d[2] = ds[2]; }
+                if (!p.dL_dscales) {
+                } else if (kRaw) {                                            // d exp(x) = exp(x) dx
                     if (p.scale_dim == 1) p.dL_dscales[i] = (ds[0] + ds[1] + ds[2]) * act_s[0];
                     else { float* d = p.dL_dscales + (size_t)i * 3; d[0] = ds[0] * act_s[0]; d[1] = ds[1] * act_s[1]; d[2] = ds[2] * act_s[2]; }
                 } else {
@@ -314,18 +338,19 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
             for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int a = 0; a < 3; ++a) Gm[k][a] = sk[k] * N[a][k];
-            if (p.dL_drotations) {
+            if (p.dL_drotations || (slot >= 0 && p.dL_ddr)) {
                 float4 dq;
                 dq.x = 2.f * qz * (Gm[0][1] - Gm[1][0]) + 2.f * qy * (Gm[2][0] - Gm[0][2]) + 2.f * qx * (Gm[1][2] - Gm[2][1]);
                 dq.y = 2.f * qy * (Gm[1][0] + Gm[0][1]) + 2.f * qz * (Gm[2][0] + Gm[0][2]) + 2.f * qr * (Gm[1][2] - Gm[2][1]) - 4.f * qx * (Gm[2][2] + Gm[1][1]);
                 dq.z = 2.f * qx * (Gm[1][0] + Gm[0][1]) + 2.f * qr * (Gm[2][0] - Gm[0][2]) + 2.f * qz * (Gm[1][2] + Gm[2][1]) - 4.f * qy * (Gm[2][2] + Gm[0][0]);
                 dq.w = 2.f * qr * (Gm[0][1] - Gm[1][0]) + 2.f * qx * (Gm[2][0] + Gm[0][2]) + 2.f * qy * (Gm[1][2] + Gm[2][1]) - 4.f * qz * (Gm[1][1] + Gm[0][0]);
-                if (kRaw) {                                                   // d normalize(x) = (g - q (q.g)) / |x|
-                    const float qg = qr * dq.x + qx * dq.y + qy * dq.z + qz * dq.w;
+                if (slot >= 0 && p.dL_ddr) reinterpret_cast<float4*>(p.dL_ddr)[slot] = dq;      // w.r.t. the offset = w.r.t. the sum
+                if (kRaw) {                                                   // d normalize(x) = (g - n (n.g)) / |x|, n = x / |x|
+                    const float qg = nr * dq.x + nx * dq.y + ny * dq.z + nz * dq.w;
                     const float inv = 1.0f / qnorm;
-                    dq.x = (dq.x - qr * qg) * inv; dq.y = (dq.y - qx * qg) * inv; dq.z = (dq.z - qy * qg) * inv; dq.w = (dq.w - qz * qg) * inv;
+                    dq.x = (dq.x - nr * qg) * inv; dq.y = (dq.y - nx * qg) * inv; dq.z = (dq.z - ny * qg) * inv; dq.w = (dq.w - nz * qg) * inv;
                 }
-                reinterpret_cast<float4*>(p.dL_drotations)[i] = dq;
+                if (p.dL_drotations) reinterpret_cast<float4*>(p.dL_drotations)[i] = dq;
             }
         } else if (p.dL_dcov3D) {
             float* d = p.dL_dcov3D + (size_t)i * 6;
@@ -335,6 +360,7 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
 
         const size_t o3 = (size_t)i * 3;
         if (p.dL_dmeans3D) { p.dL_dmeans3D[o3] = dmean.x; p.dL_dmeans3D[o3 + 1] = dmean.y; p.dL_dmeans3D[o3 + 2] = dmean.z; }
+        if (slot >= 0 && p.dL_ddx) { float* d = p.dL_ddx + (size_t)slot * 3; d[0] = dmean.x; d[1] = dmean.y; d[2] = dmean.z; }
         if (p.dL_dmeans2D) { p.dL_dmeans2D[o3] = dmean2D_x; p.dL_dmeans2D[o3 + 1] = dmean2D_y; p.dL_dmeans2D[o3 + 2] = 0.f; }
         if (p.dL_dopacity) {
             if (kRaw) {                                                      // d sigmoid(x) = o (1 - o) dx; o as the forward stored it
@@ -375,6 +401,8 @@ int launch_gaussian_backward(const G4RFrame& f, const G4RGaussians& g, const int
     p.means3D = g.means3D; p.shs = g.shs; p.shs_rest = g.shs_rest; p.colors_precomp = g.colors_precomp; p.scales = g.scales;
     p.rotations = g.rotations; p.cov3D_precomp = g.cov3D_precomp;
     p.scale_dim = g.scale_dim == 1 ? 1 : 3;
+    p.dyn_slot = g.dyn_slot; p.dx = g.dx; p.ds = g.ds; p.dr = g.dr;
+    p.dL_ddx = io.dL_ddx; p.dL_dds = io.dL_dds; p.dL_ddr = io.dL_ddr;
     p.viewmatrix = f.viewmatrix; p.projmatrix = f.projmatrix; p.projmatrix_raw = f.projmatrix_raw; p.campos = f.campos;
     p.radii = radii;
     p.rec = (const float4*)((const char*)geom + gl.rec);

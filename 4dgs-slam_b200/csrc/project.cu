@@ -22,6 +22,9 @@ struct ProjectParams {
     float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
     const float *means3D, *opacities, *shs, *shs_rest, *colors_precomp, *scales, *rotations, *cov3D_precomp;
     int scale_dim;                // raw mode: 1 = isotropic _scaling [P,1]
+    const uint8_t* mask;          // static mask / dynamic offsets (include/g4r.h), all NULL on the reference surface
+    const int32_t* dyn_slot;
+    const float *dx, *ds, *dr;
     const float *viewmatrix, *projmatrix, *campos;
     float4* rec;
     uint8_t* clamped;
@@ -91,8 +94,13 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
     __syncthreads();
     if (i >= p.P) return;
     p.n_touched[i] = 0;                          // accumulated by composite_forward_kernel
+    if (p.mask != nullptr && p.mask[i] == 0) { p.radii[i] = 0; return; }     // masked out: as if culled
 
-    const float x = s_mean[threadIdx.x * 3 + 0], y = s_mean[threadIdx.x * 3 + 1], z = s_mean[threadIdx.x * 3 + 2];
+    float x = s_mean[threadIdx.x * 3 + 0], y = s_mean[threadIdx.x * 3 + 1], z = s_mean[threadIdx.x * 3 + 2];
+    const int slot = p.dyn_slot != nullptr ? p.dyn_slot[i] : -1;              // >= 0: row of the dynamic offsets
+    if (slot >= 0 && p.dx != nullptr) {
+        x += __ldg(p.dx + (size_t)slot * 3); y += __ldg(p.dx + (size_t)slot * 3 + 1); z += __ldg(p.dx + (size_t)slot * 3 + 2);
+    }
     const float* __restrict__ Q = s_cam + 16;
     float v[16];
 #pragma unroll
@@ -118,6 +126,9 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
         float s1 = iso ? s0 : s_aux[threadIdx.x * 3 + 1];
         float s2 = iso ? s0 : s_aux[threadIdx.x * 3 + 2];
         if (kRaw) { s0 = expf(s0); s1 = iso ? s0 : expf(s1); s2 = iso ? s0 : expf(s2); }     // scaling_activation = exp
+        if (slot >= 0 && p.ds != nullptr) {          // scales + dscale (gaussian_renderer/__init__.py:167-170)
+            s0 += __ldg(p.ds + (size_t)slot * 3); s1 += __ldg(p.ds + (size_t)slot * 3 + 1); s2 += __ldg(p.ds + (size_t)slot * 3 + 2);
+        }
         const float sx = __fmul_rn(p.scale_modifier, s0);
         const float sy = __fmul_rn(p.scale_modifier, s1);
         const float sz = __fmul_rn(p.scale_modifier, s2);
@@ -125,6 +136,10 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
         if (kRaw) {                                  // rotation_activation = normalize
             const float n = g4r_quat_norm(qr, qx, qy, qz);
             qr = __fdiv_rn(qr, n); qx = __fdiv_rn(qx, n); qy = __fdiv_rn(qy, n); qz = __fdiv_rn(qz, n);
+        }
+        if (slot >= 0 && p.dr != nullptr) {          // get_rotation + drot (:171-174): added AFTER the normalisation
+            qr += __ldg(p.dr + (size_t)slot * 4); qx += __ldg(p.dr + (size_t)slot * 4 + 1);
+            qy += __ldg(p.dr + (size_t)slot * 4 + 2); qz += __ldg(p.dr + (size_t)slot * 4 + 3);
         }
         const float yy = __fmul_rn(qy, qy), zz = __fmul_rn(qz, qz);
         const float xz = __fmul_rn(qx, qz), rz = __fmul_rn(qr, qz), rx = __fmul_rn(qr, qx);
@@ -286,6 +301,7 @@ int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* i
     p.means3D = g.means3D; p.opacities = g.opacities; p.shs = g.shs; p.shs_rest = g.shs_rest; p.colors_precomp = g.colors_precomp;
     p.scales = g.scales; p.rotations = g.rotations; p.cov3D_precomp = g.cov3D_precomp;
     p.scale_dim = g.scale_dim == 1 ? 1 : 3;
+    p.mask = g.mask; p.dyn_slot = g.dyn_slot; p.dx = g.dx; p.ds = g.ds; p.dr = g.dr;
     p.viewmatrix = f.viewmatrix; p.projmatrix = f.projmatrix; p.campos = f.campos;
     p.rec = reinterpret_cast<float4*>((char*)geom + gl.rec);
     p.clamped = reinterpret_cast<uint8_t*>((char*)geom + gl.clamped);

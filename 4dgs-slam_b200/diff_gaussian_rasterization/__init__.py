@@ -33,6 +33,7 @@ __all__ = [
     "rasterize_gaussians_with_state",
     "FusedGaussianRasterizer",
     "rasterize_gaussians_raw",
+    "dynamic_slots",
     "captured_overflow",
     "reset_captured",
 ]
@@ -63,6 +64,7 @@ class _Gaussians(ctypes.Structure):
         ("colors_precomp", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("rotations", ctypes.c_void_p),
         ("cov3D_precomp", ctypes.c_void_p),
         ("shs_rest", ctypes.c_void_p), ("activation", ctypes.c_int32), ("scale_dim", ctypes.c_int32),
+        ("mask", ctypes.c_void_p), ("dyn_slot", ctypes.c_void_p), ("dx", ctypes.c_void_p), ("ds", ctypes.c_void_p), ("dr", ctypes.c_void_p),
     ]
 
 
@@ -79,7 +81,7 @@ class _BackwardIO(ctypes.Structure):
         ("dL_dmeans3D", ctypes.c_void_p), ("dL_dmeans2D", ctypes.c_void_p), ("dL_dopacity", ctypes.c_void_p),
         ("dL_dshs", ctypes.c_void_p), ("dL_dcolors_precomp", ctypes.c_void_p), ("dL_dscales", ctypes.c_void_p),
         ("dL_drotations", ctypes.c_void_p), ("dL_dcov3D", ctypes.c_void_p), ("dL_dtau", ctypes.c_void_p),
-        ("dL_dshs_rest", ctypes.c_void_p),
+        ("dL_dshs_rest", ctypes.c_void_p), ("dL_ddx", ctypes.c_void_p), ("dL_dds", ctypes.c_void_p), ("dL_ddr", ctypes.c_void_p),
     ]
 
 
@@ -233,9 +235,13 @@ def _make_frame(rs: "GaussianRasterizationSettings", device: torch.device, sh_co
     return f
 
 
-def _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw=None) -> _Gaussians:
-    """`raw` = None (reference surface: activated parameters) or (features_rest | None, scale_dim): include/g4r.h G4R_ACT_RAW."""
+def _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw=None, extra=None) -> _Gaussians:
+    """`raw` = None (reference surface: activated parameters) or (features_rest | None, scale_dim): include/g4r.h G4R_ACT_RAW.
+    `extra` = None or dict(mask=uint8 [P] | None, dyn_slot=int32 [P] | None, dx, ds, dr): the in-kernel static mask / dynamic offsets."""
     g = _Gaussians()
+    if extra is not None:
+        g.mask, g.dyn_slot = _ptr(extra.get("mask")), _ptr(extra.get("dyn_slot"))
+        g.dx, g.ds, g.dr = _ptr(extra.get("dx")), _ptr(extra.get("ds")), _ptr(extra.get("dr"))
     g.P = P
     g.means3D, g.opacities = _ptr(means3D), _ptr(opacities)
     g.shs, g.colors_precomp = _ptr(sh), _ptr(colors_precomp)
@@ -256,9 +262,9 @@ def _layout(P: int, W: int, H: int, cap: int) -> _Layout:
 # ----------------------------------------------------------------------------------------------
 # forward / backward drivers
 # ----------------------------------------------------------------------------------------------
-def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, raw=None):
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, raw=None, extra=None):
     """`raw` = None, or (features_rest tensor | None, scale_dim) when the tensors are GaussianModel's raw parameters
-    (then `sh` is _features_dc [P,1,3])."""
+    (then `sh` is _features_dc [P,1,3]).  `extra` = None or the static mask / dynamic offsets (see _make_gaussians)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:58-60
     if not means3D.is_cuda:
@@ -306,7 +312,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         ctx = _context(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         frame = _make_frame(rs, device, M, keep)
-        g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw)
+        g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw, extra)
         out = _ForwardOut(color.data_ptr(), depth.data_ptr(), opacity.data_ptr(), radii.data_ptr(), n_touched.data_ptr())
 
         key = (device.index, W, H)
@@ -357,7 +363,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
 
 
 def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, radii, geom, img, binning,
-                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None, raw=None, want=None):
+                   opacities_shape, grad_out_color, grad_out_depth, frame_keep=None, raw=None, want=None, extra=None):
     """`raw` = None or (features_rest | None, scale_dim): gradients are then w.r.t. the raw parameters and a tenth element, the
     gradient of features_rest, is appended to the returned tuple.  `want` = dict of booleans (means3D, means2D, sh,
     colors, opacities, scales, rotations, cov) from autograd's needs_input_grad: gradients nobody asked for are neither
@@ -380,9 +386,16 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
     grad_scales = torch.empty((P, raw[1] if raw is not None else 3), **f32) if scales.numel() and w("scales") else None
     grad_rot = torch.empty((P, 4), **f32) if rotations.numel() and w("rotations") else None
     grad_cov = torch.empty((P, 6), **f32) if cov3Ds_precomp.numel() and w("cov") else None
+    grad_off = [None, None, None]
+    if extra is not None and extra.get("dyn_slot") is not None:
+        for k, name in enumerate(("dx", "ds", "dr")):
+            if extra.get(name) is not None and w(name):
+                grad_off[k] = torch.empty_like(extra[name])
     if P == 0:
         tau.zero_()
         res = (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau)
+        if extra is not None:
+            return res + (grad_rest, [None if g_ is None else g_.zero_() for g_ in grad_off])
         return res + (grad_rest,) if raw is not None else res
 
     grad_out_color = _dev_f32(grad_out_color, device)
@@ -395,14 +408,16 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
         if frame is None:
             frame = _make_frame(rs, device, M, keep)
         g = _make_gaussians(P, means3D, None, sh, colors_precomp, scales, rotations, cov3Ds_precomp,
-                            None if raw is None else (raw[0], raw[1]))
+                            None if raw is None else (raw[0], raw[1]), extra)
         g.opacities = means3D.data_ptr()   # opacities are not read in backward (they live in the splat records)
         io = _BackwardIO(grad_out_color.data_ptr(), grad_out_depth.data_ptr(), _ptr(grad_means3D), _ptr(grad_means2D),
                          _ptr(grad_opacities), _ptr(grad_sh), _ptr(grad_colors), _ptr(grad_scales), _ptr(grad_rot),
-                         _ptr(grad_cov), tau.data_ptr(), _ptr(grad_rest))
+                         _ptr(grad_cov), tau.data_ptr(), _ptr(grad_rest), _ptr(grad_off[0]), _ptr(grad_off[1]), _ptr(grad_off[2]))
         _check(_lib.g4r_backward(ctypes.byref(frame), ctypes.byref(g), radii.data_ptr(), geom.data_ptr(), img.data_ptr(),
                                  binning.data_ptr(), scratch.data_ptr(), ctypes.byref(io), stream))
     res = (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau)
+    if extra is not None:
+        return res + (grad_rest, grad_off)
     return res + (grad_rest,) if raw is not None else res
 
 
@@ -560,23 +575,35 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
     (`_xyz, _features_dc, _features_rest, _opacity, _scaling, _rotation`); the activations of
     `gaussian_splatting/scene/gaussian_model.py:100-128` (sigmoid / exp / normalize / cat) run inside the projection kernel and
     their chain rule inside the per-Gaussian backward kernel, so the ~7 element-wise torch kernels of the prelude of
-    `gaussian_renderer/__init__.py:108-131` and their autograd twins disappear."""
+    `gaussian_renderer/__init__.py:108-131` and their autograd twins disappear.  Optionally the rest of that prelude too: the
+    static `mask` (`:180-191`; here a per-Gaussian flag, no gather, outputs keep the full length) and the dynamic offsets
+    `dx / ds / dr` (`:159-174`; here looked up through `dyn_slot`, no scatter into zero tensors)."""
 
     @staticmethod
-    def forward(ctx, xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta, rho, raster_settings):
+    def forward(ctx, xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta, rho, dx, ds, dr, raster_settings,
+                mask, dyn_slot):
         e = _empty()
         scale_dim = int(scaling_raw.size(1)) if scaling_raw.dim() == 2 else 0
         if scale_dim not in (1, 3):
             raise RuntimeError("scaling_raw must have dimensions (num_points, 3) or (num_points, 1)")
         if features_dc.dim() != 3 or features_dc.size(1) != 1 or features_dc.size(2) != 3:
             raise RuntimeError("features_dc must have dimensions (num_points, 1, 3)")
+        device = xyz.device
+        extra = None
+        if mask is not None or dyn_slot is not None:
+            extra = dict(mask=None if mask is None else mask.to(device=device, dtype=torch.uint8).contiguous(),
+                         dyn_slot=None if dyn_slot is None else dyn_slot.to(device=device, dtype=torch.int32).contiguous())
+            if dyn_slot is not None:
+                for name, t in (("dx", dx), ("ds", ds), ("dr", dr)):
+                    extra[name] = _dev_f32(t, device) if t is not None and t.numel() else None
         color, radii, depth, opacity, n_touched, state = _forward_impl(
-            xyz, features_dc, e, opacity_raw, scaling_raw, rotation_raw, e, raster_settings, raw=(features_rest, scale_dim))
+            xyz, features_dc, e, opacity_raw, scaling_raw, rotation_raw, e, raster_settings, raw=(features_rest, scale_dim), extra=extra)
         ctx.raster_settings = raster_settings
         ctx.P = state["P"]
         ctx.scale_dim = scale_dim
         ctx.opacities_shape = tuple(opacity_raw.shape)
         ctx.frame_keep = state.get("frame")
+        ctx.extra = extra
         ctx.save_for_backward(xyz, features_dc, features_rest, scaling_raw, rotation_raw, radii,
                               state["geom"], state["binning"], state["img"])
         ctx.mark_non_differentiable(radii, n_touched)
@@ -589,21 +616,34 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
         e = _empty()
         rest = _dev_f32(features_rest, device) if features_rest.numel() else None
         needs = ctx.needs_input_grad
-        want = dict(means3D=needs[0], means2D=needs[1], sh=needs[2] or needs[3], opacities=needs[4], scales=needs[5], rotations=needs[6])
-        (g_xyz, g_m2d, g_dc, _gc, g_op, g_sc, g_rot, _gcov, tau, g_rest) = _backward_impl(
+        want = dict(means3D=needs[0], means2D=needs[1], sh=needs[2] or needs[3], opacities=needs[4], scales=needs[5], rotations=needs[6],
+                    dx=needs[9], ds=needs[10], dr=needs[11])
+        res = _backward_impl(
             ctx.raster_settings, ctx.P, _dev_f32(xyz, device), _dev_f32(features_dc, device), e, _dev_f32(scaling_raw, device),
             _dev_f32(rotation_raw, device), e, radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth,
-            ctx.frame_keep, raw=(rest, ctx.scale_dim), want=want)
+            ctx.frame_keep, raw=(rest, ctx.scale_dim), want=want, extra=ctx.extra)
+        (g_xyz, g_m2d, g_dc, _gc, g_op, g_sc, g_rot, _gcov, tau, g_rest) = res[:10]
+        g_off = res[10] if len(res) > 10 else [None, None, None]
         if g_rest is None and features_rest.numel() == 0 and needs[3]:
             g_rest = torch.zeros_like(features_rest)
         return (g_xyz, g_m2d, g_dc, g_rest, g_op, g_sc, g_rot,
-                tau[3:6].view(1, -1) if needs[7] else None, tau[:3].view(1, -1) if needs[8] else None, None)
+                tau[3:6].view(1, -1) if needs[7] else None, tau[:3].view(1, -1) if needs[8] else None,
+                g_off[0], g_off[1], g_off[2], None, None, None)
+
+
+def dynamic_slots(dygs: torch.Tensor) -> torch.Tensor:
+    """int32 [P]: rank of every dynamic Gaussian among the dynamic ones (the row of dx / ds / dr that belongs to it), -1 for static
+    Gaussians.  `dygs` only changes when the model is densified / pruned, so callers cache this next to it."""
+    d = dygs.to(torch.int32)
+    return torch.where(dygs, torch.cumsum(d, 0, dtype=torch.int32) - 1, torch.full_like(d, -1))
 
 
 def rasterize_gaussians_raw(xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta, rho,
-                            raster_settings):
+                            raster_settings, mask=None, dx=None, ds=None, dr=None, dyn_slot=None):
+    e = _empty()
     return _RasterizeGaussiansRaw.apply(xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw,
-                                        theta, rho, raster_settings)
+                                        theta, rho, e if dx is None else dx, e if ds is None else ds, e if dr is None else dr,
+                                        raster_settings, mask, dyn_slot)
 
 
 class FusedGaussianRasterizer(nn.Module):
@@ -622,15 +662,22 @@ class FusedGaussianRasterizer(nn.Module):
         super().__init__()
         self.raster_settings = raster_settings
 
-    def forward(self, xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta=None, rho=None):
+    def forward(self, xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, theta=None, rho=None,
+                mask=None, dx=None, ds=None, dr=None, dyn_slot=None):
+        """`mask` (bool / uint8 [P]): Gaussians with mask == 0 are skipped inside the kernels -- the in-place version of
+        `render(mask=...)`; `radii` / `n_touched` keep the FULL length P (the reference returns the gathered length).
+        `dx, ds, dr` ([Pd,3], [Pd,3], [Pd,4]) + `dyn_slot` (`dynamic_slots(pc.dygs)`): the per-dynamic-Gaussian offsets of
+        `render(dx=, ds=, dr=)`, added after the activations like the reference does."""
         if features_rest is None:
             features_rest = _empty()
         if theta is None:
             theta = _empty()
         if rho is None:
             rho = _empty()
+        if (dx is not None or ds is not None or dr is not None) and dyn_slot is None:
+            raise Exception("dx / ds / dr need dyn_slot = dynamic_slots(dygs)")
         return rasterize_gaussians_raw(xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw,
-                                       theta, rho, self.raster_settings)
+                                       theta, rho, self.raster_settings, mask=mask, dx=dx, ds=ds, dr=dr, dyn_slot=dyn_slot)
 
 
 # ----------------------------------------------------------------------------------------------

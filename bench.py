@@ -356,11 +356,18 @@ def run_slam_shape(args, dgr, lib, device, rank, world, barrier, ref_cuda):
     popts = [S.pose_optimizer(v) for v in views]
     result_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
+    fused = [False]
+    frozen = tuple(p.detach() for p in pc.parameters())           # tracking never updates the map
+    static_mask = (pc.dygs == False).to(torch.uint8)              # noqa: E712
+
     def step(from_host=False):
         if from_host:
             for v, (im, dp) in zip(views, gt_host):
                 v.original_image, v.depth_gt = im.to(device, non_blocking=True), dp.to(device, non_blocking=True)
-        if mapping:
+        if fused[0]:
+            loss = (S.mapping_iteration_fused(dgr, views, pc, bg, gopt, popts) if mapping
+                    else S.tracking_iteration_fused(dgr, views[0], frozen, static_mask, bg, popts[0]))
+        elif mapping:
             loss = S.mapping_iteration(dgr, render_fn, views, pc, bg, gopt, popts)
         else:
             loss = S.tracking_iteration(dgr, render_fn, views[0], pc, bg, popts[0], gopt)
@@ -404,6 +411,18 @@ def run_slam_shape(args, dgr, lib, device, rank, world, barrier, ref_cuda):
     if world > 1:
         dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
     e2e_value = world * K2 * views_n / (float(t_h.item()) / 1000.0)
+    # the same loop body on the opt-in fused API of this repo (raw parameters + in-kernel mask, fused loss, pose-only backward)
+    fused_rec = None
+    if lib is not None:
+        fused[0] = True
+        fms, _ = timed_steps(step, steps, args.warmup, flush, barrier, None)
+        t_f = torch.tensor([sum(fms)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t_f, op=dist.ReduceOp.MAX)
+        fused_rec = {"value": world * steps * views_n / (float(t_f.item()) / 1000.0), "unit": "frames/s", "ms_per_step": float(t_f.item()) / steps,
+                     "api": "FusedGaussianRasterizer (raw parameters, in-kernel static mask) + slam_loss (one kernel) + "
+                            + ("pose-only backward" if not mapping else "Adam") + "; camera matrices evaluated once per render"}
+        fused[0] = False
     if rank != 0:
         return
     h2d = sum(im.numel() * 4 + dp.numel() * 4 for im, dp in gt_host)
@@ -426,6 +445,8 @@ def run_slam_shape(args, dgr, lib, device, rank, world, barrier, ref_cuda):
     }
     if ref_cuda:
         line["impl"] = "reference"
+    if fused_rec is not None:
+        line["fused_api"] = fused_rec
     if stage:
         line["kernel_ms"] = {k: round(v[0], 5) for k, v in stage.items()}
         line["kernel_launches_per_step"] = {k: round(v[1] / (steps + args.warmup), 2) for k, v in stage.items()}

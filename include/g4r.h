@@ -102,6 +102,18 @@ typedef struct G4RGaussians {
     const float* shs_rest;        /* [P,M-1,3] or NULL; only read when activation == G4R_ACT_RAW */
     int32_t activation;           /* G4R_ACT_NONE (reference surface) or G4R_ACT_RAW */
     int32_t scale_dim;            /* raw mode: 3, or 1 for an isotropic _scaling [P,1]; 0 means 3 */
+    /* ---- static mask + dynamic offsets (opt-in; the rest of render()'s prelude, gaussian_renderer/__init__.py:159-191) ----
+     * The reference gathers every per-Gaussian tensor with a boolean mask before the call (tracking renders only the static
+     * Gaussians, utils/slam_frontend.py:412-414) and scatters per-dynamic-Gaussian offsets into zero tensors that it adds to the
+     * positions / activated scales / activated rotations (:163-174).  Here the kernels do both in place:
+     *   mask[i] == 0        -> Gaussian i is skipped (radius 0, zero gradients); outputs keep the FULL length P
+     *   dyn_slot[i] = k >= 0 -> means3D[i] += dx[k], scale[i] += ds[k] (after exp), rotation[i] += dr[k] (after normalize);
+     *                          k = rank of i among the dynamic Gaussians (cumsum(dygs) - 1), -1 for static ones. */
+    const uint8_t* mask;          /* [P] or NULL */
+    const int32_t* dyn_slot;      /* [P] or NULL */
+    const float* dx;              /* [Pd,3] or NULL */
+    const float* ds;              /* [Pd,3] or NULL */
+    const float* dr;              /* [Pd,4] or NULL */
 } G4RGaussians;
 
 /* Forward outputs (DEVICE pointers, written in full; no pre-zeroing needed). */
@@ -134,6 +146,9 @@ typedef struct G4RBackwardIO {
     float* dL_dcov3D;             /* [P,6]   or NULL (only when cov3D_precomp was given) */
     float* dL_dtau;               /* [8]: [0:3] = grad_rho, [3:6] = grad_theta, [6:8] padding */
     float* dL_dshs_rest;          /* [P,M-1,3] or NULL; raw mode only (then dL_dshs is [P,1,3], dL_dscales [P,scale_dim]) */
+    float* dL_ddx;                /* [Pd,3] or NULL: gradients of the dynamic offsets (rows of Gaussians with dyn_slot >= 0) */
+    float* dL_dds;                /* [Pd,3] or NULL */
+    float* dL_ddr;                /* [Pd,4] or NULL */
 } G4RBackwardIO;
 
 typedef struct G4RContext G4RContext;   /* owns one pinned int + one event; one per host thread/device */
@@ -285,6 +300,29 @@ int g4r_backward_composite(const G4RFrame* frame, int32_t P_all, const void* geo
                            const float* dL_dcolor, const float* dL_ddepth, void* acc, void* stream);
 int g4r_backward_gaussians(const G4RFrame* frame, const G4RGaussians* g, const int32_t* radii, const void* geom,
                            const void* acc, const G4RBackwardIO* io, void* stream);
+
+/* ---- fused RGB-D losses of the tracking / mapping loops (opt-in) -----------------------------------
+ * get_loss_tracking_rgbd (utils/slam_utils.py:57-173; mode 0) and get_loss_mapping_rgbd (:252-364, static non-split branch;
+ * mode 1) with their image gradients in one kernel: writes dL_dimage [3,H,W], dL_ddepth [1,H,W] and out4 = {loss, dL/d
+ * exposure_a, dL/d exposure_b, 0}.  Masks are uint8 [H,W] (non-zero = keep) or NULL; exposure pointers may be NULL (a = b = 0).
+ * scratch32 = 32 bytes of device scratch.  The rendered opacity weights the tracking RGB term as a constant (the rasterizer
+ * drops its gradient, DGR/diff_gaussian_rasterization/__init__.py:108). */
+typedef struct G4RLossIn {
+    int32_t width, height;
+    int32_t mode;                 /* 0 tracking, 1 mapping */
+    float   alpha;                /* weight of the RGB term (config Training.alpha, default 0.95) */
+    float   rgb_boundary_threshold;
+    const float* image;           /* [3,H,W] rendered colour */
+    const float* depth;           /* [1,H,W] rendered depth */
+    const float* opacity;         /* [1,H,W] rendered opacity (tracking) or NULL */
+    const float* gt_image;        /* [3,H,W] */
+    const float* gt_depth;        /* [1,H,W] */
+    const float* exposure_a;      /* [1] or NULL */
+    const float* exposure_b;      /* [1] or NULL */
+    const uint8_t* motion_mask;   /* [H,W] or NULL */
+    const uint8_t* grad_mask;     /* [H,W] or NULL (tracking only) */
+} G4RLossIn;
+int g4r_slam_loss(const G4RLossIn* in, float* dL_dimage, float* dL_ddepth, float* out4, void* scratch32, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------- */
 int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

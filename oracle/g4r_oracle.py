@@ -208,3 +208,52 @@ def raw_chain_rule(act: dict, grads: dict, scale_dim: int = 3) -> dict:
     gsh = grads["dL_dshs"]
     return dict(dL_dopacity_raw=grads["dL_dopacity"].astype(np.float64).reshape(-1) * o * (1.0 - o), dL_dscaling_raw=gs,
                 dL_drotation_raw=gq, dL_dfeatures_dc=gsh[:, :1], dL_dfeatures_rest=gsh[:, 1:])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused SLAM losses: numpy restatement of utils/slam_utils.py, pinned to tests/golden/slam_loss.npz
+# (vectors produced by the reference's own functions + torch autograd, tools/make_loss_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def slam_loss_ref(mode: str, image, depth, gt_image, gt_depth, opacity=None, exposure=(0.0, 0.0), motion_mask=None, grad_mask=None,
+                  alpha: float = 0.95, thr: float = 0.01) -> dict:
+    """get_loss_tracking -> get_loss_tracking_rgbd (slam_utils.py:57-173; mode "tracking") or get_loss_mapping ->
+    get_loss_mapping_rgbd (:252-364, static non-split branch; mode "mapping") in float64, with the closed-form gradients
+    w.r.t. the rendered colour, depth and the exposure pair.  `motion_mask=None` = the reference's "mask not applied" case."""
+    f = np.float64
+    image, depth = np.asarray(image, f).reshape(3, -1), np.asarray(depth, f).reshape(-1)
+    gt, gd = np.asarray(gt_image, np.float32).reshape(3, -1), np.asarray(gt_depth, f).reshape(-1)
+    X = depth.size
+    a, b = float(exposure[0]), float(exposure[1])
+    ea = np.exp(a)
+    mm = np.ones(X, f) if motion_mask is None else (np.asarray(motion_mask).reshape(-1) != 0).astype(f)
+    m = ((gt[0] + gt[1]) + gt[2] > np.float32(thr)).astype(f) * mm                  # gt_image.sum(dim=0) > rgb_boundary_threshold (float32)
+    gt = gt.astype(f)
+    if mode == "tracking":
+        o = np.asarray(opacity, f).reshape(-1)
+        if grad_mask is not None:
+            m = m * (np.asarray(grad_mask).reshape(-1) != 0)
+        w = o
+        md = ((gd > 0.01) & (gd < 1000.0) & (np.asarray(opacity, np.float32).reshape(-1) > np.float32(0.95))).astype(f) * mm
+    else:
+        w = np.ones(X, f)
+        md = ((gd > 0.01) & (gd < 10000.0)).astype(f) * mm
+    diff = (ea * image + b) * m - gt * m
+    s = np.sign(diff) * m * w
+    dd = depth * md - gd * md
+    k_rgb, k_d = alpha / (3.0 * X), (1.0 - alpha) / X
+    return dict(loss=k_rgb * (w * np.abs(diff)).sum() + k_d * np.abs(dd).sum(), d_image=(k_rgb * s * ea).reshape(np.shape(image)),
+                d_depth=k_d * np.sign(dd) * md, d_exposure=np.array([k_rgb * (s * ea * image).sum(), k_rgb * s.sum()]))
+
+
+def prelude_ref(xyz, scaling_act, rotation_act, dygs, dx=None, ds=None, dr=None, mask=None) -> dict:
+    """The remaining prelude of render() (gaussian_renderer/__init__.py:159-191) in numpy: dynamic offsets scattered into the rows
+    of the dynamic Gaussians and added to positions / ACTIVATED scales / ACTIVATED rotations, then the static-mask gather.
+    Returns the tensors the rasterizer receives plus the row indices kept by the mask."""
+    xyz, sc, rot = np.array(xyz, copy=True), np.array(scaling_act, copy=True), np.array(rotation_act, copy=True)
+    dy = np.asarray(dygs).astype(bool)
+    if dx is not None and ds is not None and dr is not None:
+        xyz[dy] += np.asarray(dx)
+        sc[dy] += np.asarray(ds)
+        rot[dy] += np.asarray(dr)
+    keep = np.arange(xyz.shape[0]) if mask is None else np.nonzero(np.asarray(mask).astype(bool))[0]
+    return dict(means3D=xyz[keep], scales=sc[keep], rotations=rot[keep], keep=keep)

@@ -298,3 +298,70 @@ def mapping_iteration(dgr, render_fn, viewpoints, gaussians, bg, gauss_opt, pose
             po.zero_grad(set_to_none=True)
             update_pose(vp)
     return loss_mapping
+
+
+# ---- the same loop bodies on the opt-in fused API ------------------------------------------------------
+def camera_matrices_once(vp):
+    """The three camera tensors of the raster settings from ONE evaluation of world_view_transform (the reference's Camera
+    properties recompute it -- two linalg.inv each time -- for viewmatrix, full_proj_transform and camera_center,
+    utils/camera_utils.py:124-148: seven 4x4 inversions per render)."""
+    view = vp.world_view_transform
+    proj = view.unsqueeze(0).bmm(vp.projection_matrix.unsqueeze(0)).squeeze(0)
+    return view, proj, view.inverse()[3, :3]
+
+
+def render_fused(dgr, vp, params, bg, sh_degree=0, mask=None, with_screenspace_grad=True):
+    """render() on FusedGaussianRasterizer: raw parameters in (activations, cat, mask gather inside the kernels).
+    `params` = (xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw)."""
+    view, proj, campos = camera_matrices_once(vp)
+    rs = dgr.GaussianRasterizationSettings(
+        image_height=int(vp.image_height), image_width=int(vp.image_width), tanfovx=math.tan(vp.FoVx * 0.5), tanfovy=math.tan(vp.FoVy * 0.5),
+        bg=bg, scale_modifier=1.0, viewmatrix=view, projmatrix=proj, projmatrix_raw=vp.projection_matrix, sh_degree=sh_degree, campos=campos,
+        prefiltered=False, debug=False)
+    xyz, f_dc, f_rest, opacity, scaling, rotation = params
+    screenspace_points = torch.zeros_like(xyz, requires_grad=with_screenspace_grad)
+    image, radii, depth, opacity_img, n_touched = dgr.FusedGaussianRasterizer(rs)(
+        xyz=xyz, means2D=screenspace_points, features_dc=f_dc, features_rest=f_rest, opacity_raw=opacity, scaling_raw=scaling,
+        rotation_raw=rotation, theta=vp.cam_rot_delta, rho=vp.cam_trans_delta, mask=mask)
+    return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii, "depth": depth,
+            "opacity": opacity_img, "n_touched": n_touched}
+
+
+def tracking_iteration_fused(dgr, viewpoint, frozen_params, static_mask, bg, opt, sh_degree=0):
+    """utils/slam_frontend.py:411-448 on the fused API: the map is frozen during tracking, so the (detached) raw parameters and
+    the static mask are prepared once per frame; per iteration: one masked render, one loss kernel, a pose-only backward (no
+    per-Gaussian gradient is computed, let alone zeroed afterwards), pose Adam step, SE(3) update."""
+    from diff_gaussian_rasterization.losses import slam_loss
+    pkg = render_fused(dgr, viewpoint, frozen_params, bg, sh_degree=sh_degree, mask=static_mask, with_screenspace_grad=False)
+    loss = slam_loss("tracking", pkg["render"], pkg["depth"], viewpoint.original_image, viewpoint.depth_gt, opacity=pkg["opacity"],
+                     exposure_a=viewpoint.exposure_a, exposure_b=viewpoint.exposure_b,
+                     motion_mask=viewpoint.motion_mask if viewpoint.uid > 0 else None, grad_mask=viewpoint.grad_mask,
+                     alpha=ALPHA, rgb_boundary_threshold=RGB_BOUNDARY_THRESHOLD)
+    loss.backward()
+    with torch.no_grad():
+        opt.step()
+        opt.zero_grad()
+        update_pose(viewpoint)
+    return loss
+
+
+def mapping_iteration_fused(dgr, viewpoints, gaussians, bg, gauss_opt, pose_opts):
+    """utils/slam_backend.py:357-771 on the fused API: per view one fused render (no torch prelude) and one loss kernel."""
+    from diff_gaussian_rasterization.losses import slam_loss
+    loss_mapping = 0
+    params = tuple(gaussians.parameters()[i] for i in (0, 1, 2, 3, 4, 5))
+    for vp in viewpoints:
+        pkg = render_fused(dgr, vp, params, bg, sh_degree=gaussians.active_sh_degree)
+        loss_mapping = loss_mapping + slam_loss("mapping", pkg["render"], pkg["depth"], vp.original_image, vp.depth_gt,
+                                                exposure_a=vp.exposure_a, exposure_b=vp.exposure_b, motion_mask=vp.motion_mask, alpha=ALPHA,
+                                                rgb_boundary_threshold=RGB_BOUNDARY_THRESHOLD)
+    loss_mapping = loss_mapping + 10 * isotropic_loss(gaussians.get_scaling)
+    loss_mapping.backward(retain_graph=True)
+    with torch.no_grad():
+        gauss_opt.step()
+        gauss_opt.zero_grad(set_to_none=True)
+        for vp, po in zip(viewpoints, pose_opts):
+            po.step()
+            po.zero_grad(set_to_none=True)
+            update_pose(vp)
+    return loss_mapping
