@@ -90,7 +90,7 @@ def _load_golden(path):
     return sc, ref
 
 
-GOLDENS = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+GOLDENS = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "g[0-9]_*.npz")))       # rasterizer fixtures (slam_loss.npz is the loss fixture)
 
 
 @pytest.mark.parametrize("path", GOLDENS, ids=[os.path.basename(p) for p in GOLDENS])
