@@ -13,7 +13,7 @@ import pytest
 from oracle.g4r_oracle import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDENS = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+GOLDENS = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "g[0-9]_*.npz")))
 
 
 def test_golden_fixtures_are_present():
