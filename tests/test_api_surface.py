@@ -90,7 +90,10 @@ def test_fused_rasterizer_surface_and_argument_checks():
     assert "FusedGaussianRasterizer" in dgr.__all__ and "rasterize_gaussians_raw" in dgr.__all__
     sig = inspect.signature(dgr.FusedGaussianRasterizer.forward)
     assert list(sig.parameters)[1:] == ["xyz", "means2D", "features_dc", "features_rest", "opacity_raw", "scaling_raw", "rotation_raw",
-                                        "theta", "rho"]
+                                        "theta", "rho", "mask", "dx", "ds", "dr", "dyn_slot"]
+    assert "dynamic_slots" in dgr.__all__
+    slots = dgr.dynamic_slots(torch.tensor([False, True, True, False, True]))
+    assert slots.tolist() == [-1, 0, 1, -1, 2] and slots.dtype is torch.int32
     rs = dgr.GaussianRasterizationSettings(image_height=8, image_width=8, tanfovx=1.0, tanfovy=1.0, bg=torch.ones(3), scale_modifier=1.0,
                                            viewmatrix=torch.eye(4), projmatrix=torch.eye(4), projmatrix_raw=torch.eye(4), sh_degree=0,
                                            campos=torch.zeros(3), prefiltered=False, debug=False)
