@@ -37,10 +37,21 @@ def test_strip_bounds_partition_the_tile_rows(tiles_y, world):
     assert prev == tiles_y
 
 
-@settings(max_examples=60, deadline=None)
-@given(W=st.integers(1, 2000), H=st.integers(1, 1200), world=st.integers(1, 8))
-def test_interleaved_tiles_are_owned_exactly_once(W, H, world):
-    masks = [sharded.owned_tiles(W, H, world, r) for r in range(world)]
-    total = sum(m.to(int) for m in masks)
-    assert int(total.min()) == 1 and int(total.max()) == 1
-    assert masks[0].numel() == ((W + 15) // 16) * ((H + 15) // 16)
+@settings(max_examples=100, deadline=None)
+@given(H=st.integers(1, 2400), world=st.integers(1, 16), cap=st.integers(1, 10_000_000), W=st.integers(1, 4000))
+def test_strips_cover_every_pixel_row_once_and_payload_sizes_are_consistent(H, world, cap, W):
+    """The pixel-row strips [16 b, min(H, 16 e)) derived from the tile-row strips tile the image, the padded strip height bounds
+    every strip, and collective_bytes reports what the slabs / strips actually hold."""
+    tiles_y, maxh = sharded._strip_rows(H, world)
+    covered = 0
+    for r in range(world):
+        b, e = sharded.strip_bounds(tiles_y, world, r)
+        y0, y1 = 16 * b, min(H, 16 * e)
+        assert y0 == min(covered, 16 * b) or y1 <= y0
+        if y1 > y0:
+            assert y0 == covered and y1 - y0 <= maxh
+            covered = y1
+    assert covered == H
+    cb = sharded.collective_bytes(W, H, world, cap)
+    assert cb["all_to_all_records"] == world * (cap + 1) * 48 == cb["all_to_all_accumulators"]
+    assert cb["all_gather_strip_ntouched_counts"] >= 5 * maxh * W * 4
