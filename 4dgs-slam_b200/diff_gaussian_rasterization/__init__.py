@@ -299,11 +299,10 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         state = dict(P=0, N=0, geom=torch.empty(0, **u8), img=torch.empty(0, **u8), binning=torch.empty(0, **u8), capacity=0)
         return z((3, H, W), **f32), torch.zeros((0,), **i32), z((1, H, W), **f32), z((1, H, W), **f32), torch.zeros((0,), **i32), state
 
-    color = torch.empty((3, H, W), **f32)
-    depth = torch.empty((1, H, W), **f32)
-    opacity = torch.empty((1, H, W), **f32)
-    radii = torch.empty((P,), **i32)
-    n_touched = torch.empty((P,), **i32)
+    # Phase 1 needs only the per-Gaussian state: it is enqueued first, and the host allocates everything phase 2 writes while
+    # the projection kernel already runs (the GPU is idle at this point whenever the caller is host-bound, e.g. during tracking).
+    ints = torch.empty((2, P), **i32)                       # radii | n_touched
+    radii, n_touched = ints[0], ints[1]
     geom = torch.empty((_lib.g4r_geom_bytes(P),), **u8)
     img = torch.empty((_lib.g4r_image_bytes(W, H),), **u8)
 
@@ -313,20 +312,26 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         stream = torch.cuda.current_stream(device).cuda_stream
         frame = _make_frame(rs, device, M, keep)
         g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw, extra)
+        capturing = torch.cuda.is_current_stream_capturing()
+        _check(_lib.g4r_forward_project(None if capturing else ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
+                                        radii.data_ptr(), n_touched.data_ptr(), stream))
+        # three separate tensors like the reference's: views of one buffer would make an in-place operation on any of them an
+        # autograd error ("a view ... of a function that returns multiple views")
+        color = torch.empty((3, H, W), **f32)
+        depth = torch.empty((1, H, W), **f32)
+        opacity = torch.empty((1, H, W), **f32)
         out = _ForwardOut(color.data_ptr(), depth.data_ptr(), opacity.data_ptr(), radii.data_ptr(), n_touched.data_ptr())
 
         key = (device.index, W, H)
         with _state_lock:
             hint = _cap_hint.get(key, 0)
-        if torch.cuda.is_current_stream_capturing():
+        if capturing:
             # CUDA-graph capture (torch.cuda.graph around forward + loss + backward): no host read-back is possible, so
             # phase 2 gets a generous fixed capacity derived from the eager warm-up iterations.  A replay whose instance
             # count outgrows it leaves the outputs untouched, its backward returns zeros, and `captured_overflow()` reports it.
             cap = int(max(hint, 4 * P) * _GRAPH_CAPACITY_FACTOR) + 4096
             binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
             sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), **u8)
-            _check(_lib.g4r_forward_project(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
-                                            radii.data_ptr(), n_touched.data_ptr(), stream))
             _check(_lib.g4r_forward_render(None, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                            binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
             if raw is not None and raw[0] is not None:
@@ -334,8 +339,6 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
             state = dict(P=P, N=-1, geom=geom, img=img, binning=binning, capacity=cap, frame=(frame, keep))
             return color, radii, depth, opacity, n_touched, state
 
-        _check(_lib.g4r_forward_project(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
-                                        radii.data_ptr(), n_touched.data_ptr(), stream))
         # Phase 2 is enqueued with a speculative capacity; N is checked only after everything is in the
         # stream, so the device never waits for the host (the reference blocks on a cudaMemcpy instead,
         # rasterizer_impl.cu:284).  `binning` (the sorted id list) is saved for backward; `sort_scratch` (the unsorted
