@@ -449,6 +449,24 @@ def native_comm(group, dev):
     return out.value
 
 
+def _settle(st: dict, nctx) -> None:
+    """Deferred mode: read the two early events of the last frame rendered with this state (they fired long ago, so this does
+    not block), update the capacity hints, and raise if that frame had outgrown its buffers -- its outputs were invalid."""
+    pend = st.get("pending")
+    if pend is None:
+        return
+    st["pending"] = None
+    N, worst = ctypes.c_int64(), ctypes.c_int64()
+    _check(_lib.g4r_shard_forward_wait(nctx, ctypes.byref(N), ctypes.byref(worst)))
+    N, worst = int(N.value), int(worst.value)
+    st["pair_hint"] = max(worst, int(st["pair_hint"] * 0.95))
+    st["n_hint"] = max(N, int(st["n_hint"] * 0.95))
+    if worst > pend[0] or N > pend[1]:
+        st["redos"] += 1
+        raise RuntimeError(f"sharded render (deferred check): the previous frame outgrew its buffers (pair count {worst} > {pend[0]} or "
+                           f"instances {N} > {pend[1]}); its outputs were invalid.  The capacities have been raised: render that frame again")
+
+
 def _sticky(st: dict, key: str, need: int, limit: int) -> int:
     """Capacity with hysteresis: grows to 1.25 x need (rounded up to 4096) when the current one is too small and only shrinks when
     the need falls below half of it.  Identical on all ranks for the pair capacity (every rank sees the same `need`).  Stable
@@ -464,7 +482,7 @@ def _sticky(st: dict, key: str, need: int, limit: int) -> int:
 
 class _ShardedRasterizeNative(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs, group):
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs, group, deferred):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         dev = means3D.device
         H, W = int(rs.image_height), int(rs.image_width)
@@ -525,7 +543,15 @@ class _ShardedRasterizeNative(torch.autograd.Function):
                                   payload.data_ptr(), strip_elems, maxh, counts_offset, payload_elems, gathered.data_ptr(), images.data_ptr(),
                                   img_state.data_ptr(), binning.data_ptr(), sort_scratch.data_ptr(), all_i.data_ptr(),
                                   all_i.data_ptr() + 4 * world * rows)
+                _settle(st, nctx)           # a deferred check of the previous frame (raises if that frame had overflowed)
                 _check(_lib.g4r_shard_forward_a(comm, nctx, ctypes.byref(full), ctypes.byref(strip), ctypes.byref(g), ctypes.byref(b), stream))
+                if deferred and st["pair_hint"] > 0 and st["n_hint"] > 0:
+                    # Deferred check: nothing is read back now.  The two early events of this frame are examined when the next
+                    # forward (or this frame's backward) starts -- by then they have long fired -- so the host never waits on the
+                    # device inside a frame and runs a whole frame ahead.  Capacities carry >= 25 % headroom with hysteresis.
+                    st["pending"] = (cap, cap_n)
+                    _check(_lib.g4r_shard_forward_b(comm, ctypes.byref(full), P, ctypes.byref(b), stream))
+                    break
                 N, worst = ctypes.c_int64(), ctypes.c_int64()
                 _check(_lib.g4r_shard_forward_wait(nctx, ctypes.byref(N), ctypes.byref(worst)))
                 N, worst = int(N.value), int(worst.value)
@@ -545,6 +571,7 @@ class _ShardedRasterizeNative(torch.autograd.Function):
                 break
             else:
                 raise RuntimeError("sharded render: slab capacity kept overflowing")
+        ctx.settle = (st, nctx)
         ctx.rs, ctx.group, ctx.P, ctx.M, ctx.world, ctx.rank, ctx.cap, ctx.cap_n = rs, group, P, M, world, rank, cap, cap_n
         ctx.frames = (full, strip, keep)
         ctx.opacities_shape = tuple(opacities.shape)
@@ -559,6 +586,7 @@ class _ShardedRasterizeNative(torch.autograd.Function):
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_opacity, grad_ntouched):
         means3D, sh, colors_precomp, scales, rotations, cov3Ds_precomp, local_i, geom_local, slabs, img_state, slots, binning = ctx.saved_tensors
         group, P, M, world, rank, cap = ctx.group, ctx.P, ctx.M, ctx.world, ctx.rank, ctx.cap
+        _settle(*ctx.settle)             # deferred mode: the forward's capacity check, now that its events have fired
         full, strip, _keep = ctx.frames
         dev = means3D.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -595,7 +623,7 @@ class _ShardedRasterizeNative(torch.autograd.Function):
                                            stream))
         return (grads["means3D"], grads["means2D"], grads.get("sh"), grads.get("colors"), grads["opacities"], grads.get("scales"),
                 grads.get("rots"), grads.get("cov"), tau[3:6].view(1, -1) if needs[8] else None, tau[:3].view(1, -1) if needs[9] else None,
-                None, None)
+                None, None, None)
 
 
 class ShardedGaussianRasterizer(torch.nn.Module):
@@ -603,7 +631,8 @@ class ShardedGaussianRasterizer(torch.nn.Module):
     full image on every rank and the local ``radii`` / ``n_touched``.  The image gradients handed to backward must be
     identical on all ranks (every rank evaluates the loss on the full image)."""
 
-    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "alltoall", native: bool = True):
+    def __init__(self, raster_settings: GaussianRasterizationSettings, group=None, backend=None, exchange: str = "alltoall", native: bool = True,
+                 deferred_check: bool = False):
         """`backend` = None: the CUDA library.  `native` (only without an injected backend): True = the frame is enqueued by the
         native runtime of csrc/shard_nccl.cu (own NCCL communicator, 4 C calls per fwd+bwd); False = the same steps orchestrated
         from Python through torch.distributed (the path the gloo tests exercise with a CPU backend)."""
@@ -613,6 +642,11 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         self.raster_settings = raster_settings
         self.group = group
         self.native = bool(native) and backend is None and os.environ.get("G4R_SHARD_NATIVE", "1") != "0"      # env: A/B switch
+        # deferred_check (native runtime only): the capacity checks of a frame are made when the NEXT frame (or this frame's
+        # backward) starts instead of in the middle of the forward, so the host never waits for the device inside a frame.
+        # A frame that outgrew its buffers then raises one call late (its outputs were invalid) -- for loops whose instance
+        # counts drift slowly (SLAM mapping) and that can re-render a frame.
+        self.deferred = bool(deferred_check) or os.environ.get("G4R_SHARD_DEFERRED", "0") == "1"
         self.backend = backend if backend is not None else CudaBackend()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
@@ -624,6 +658,6 @@ class ShardedGaussianRasterizer(torch.nn.Module):
         e = lambda t: torch.Tensor([]) if t is None else t
         if self.native:
             return _ShardedRasterizeNative.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
-                                                 e(theta), e(rho), self.raster_settings, self.group)
+                                                 e(theta), e(rho), self.raster_settings, self.group, self.deferred)
         return _ShardedRasterize.apply(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations), e(cov3D_precomp),
                                        e(theta), e(rho), self.raster_settings, self.group, self.backend)
