@@ -16,6 +16,11 @@ for stage in "$@"; do
     smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "rc=$?" ;;
     memcheck) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/memcheck.log 2>&1; echo "rc=$?" ;;
     racecheck) timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/racecheck.log 2>&1; echo "rc=$?" ;;
+    initcheck) timeout 900 compute-sanitizer --tool initcheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/initcheck.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/initcheck.log ;;
+    memory)   timeout 600 python tools/retained_memory.py > gpurun_out/retained_memory.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/retained_memory.log | cut -c1-900 ;;
+    benchmore) for wl in C2 C3sh3; do for impl in ours reference; do
+                timeout 600 python bench.py --workload $wl --impl $impl --steps 100 --no-cpu-baseline > gpurun_out/bench_${wl}_${impl}.json 2> gpurun_out/bench_${wl}_${impl}.err; echo "$wl $impl rc=$?"; cut -c1-300 gpurun_out/bench_${wl}_${impl}.json
+              done; done ;;
     bench)    timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; cat gpurun_out/bench.json ;;
     benchref) timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches.log 2>&1; echo "rc=$?" ;;

@@ -1,4 +1,6 @@
-"""Small forward+backward cases for compute-sanitizer (memcheck / racecheck)."""
+"""Small forward+backward cases for compute-sanitizer (memcheck / racecheck / initcheck): the standard path on three scene
+types (SH 3; precomputed colour + covariance; oversized tiles -> global-memory radix sort), the raw-parameter path with the
+in-kernel mask and dynamic offsets, and the fused loss kernel."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,4 +14,27 @@ for kw in (dict(P=700, W=100, H=75, sh_degree=3, seed=1), dict(P=500, W=64, H=48
     out = runners.run_g4r(make_scene(**kw).to(dev))
     torch.cuda.synchronize()
     print(kw, "N", out["num_rendered"])
+
+import diff_gaussian_rasterization as dgr
+from diff_gaussian_rasterization.losses import slam_loss
+sc = make_scene(900, 96, 64, sh_degree=1, seed=4).to(dev)
+raw = runners.raw_parameters(sc, seed=2)
+g = torch.Generator().manual_seed(1)
+dygs = (torch.rand(sc.P, generator=g) < 0.3).to(dev)
+nd = int(dygs.sum())
+leaf = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+off = [t.to(dev).requires_grad_(True) for t in (0.01 * torch.randn(nd, 3, generator=g), 0.001 * torch.rand(nd, 3, generator=g), 0.01 * torch.randn(nd, 4, generator=g))]
+m2d = torch.zeros_like(leaf["xyz"], requires_grad=True)
+theta, rho = torch.zeros(3, device=dev, requires_grad=True), torch.zeros(3, device=dev, requires_grad=True)
+color, radii, depth, opacity, n_touched = dgr.FusedGaussianRasterizer(runners.settings_for(sc, dgr))(
+    xyz=leaf["xyz"], means2D=m2d, features_dc=leaf["dc"], features_rest=leaf["rest"], opacity_raw=leaf["opacity"], scaling_raw=leaf["scaling"],
+    rotation_raw=leaf["rotation"], theta=theta, rho=rho, mask=torch.rand(sc.P, generator=g).to(dev) > 0.2, dx=off[0], ds=off[1], dr=off[2],
+    dyn_slot=dgr.dynamic_slots(dygs))
+ea, eb = torch.tensor([0.05], device=dev, requires_grad=True), torch.tensor([0.01], device=dev, requires_grad=True)
+loss = slam_loss("tracking", color, depth, torch.rand(3, sc.H, sc.W, generator=g).to(dev), (3 * torch.rand(1, sc.H, sc.W, generator=g)).to(dev),
+                 opacity=opacity, exposure_a=ea, exposure_b=eb, motion_mask=(torch.rand(sc.H, sc.W, generator=g) > 0.3).to(dev),
+                 grad_mask=(torch.rand(1, sc.H, sc.W, generator=g) > 0.1).to(dev))
+loss.backward()
+torch.cuda.synchronize()
+print("fused path loss", float(loss.detach()))
 print("sanitize cases done")
