@@ -204,6 +204,39 @@ def reset_captured() -> None:
     captured_overflow()
 
 
+class _on_device:
+    """`with torch.cuda.device(d)` costs two cudaSetDevice round trips (~10 us); nearly every call already runs on the tensors'
+    device, so the guard is only entered when it is needed."""
+    __slots__ = ("guard",)
+
+    def __init__(self, device: torch.device):
+        idx = device.index
+        self.guard = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
+
+
+_size_cache: dict = {}
+
+
+def _bytes(fn_name: str, *args) -> int:
+    """Scratch sizes from the library, memoised (they are pure functions of their arguments)."""
+    key = (fn_name,) + args
+    v = _size_cache.get(key)
+    if v is None:
+        if len(_size_cache) > 4096:
+            _size_cache.clear()
+        v = _size_cache[key] = int(getattr(_lib, fn_name)(*args))
+    return v
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None or t.numel() == 0:
         return None
@@ -303,11 +336,11 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
     # the projection kernel already runs (the GPU is idle at this point whenever the caller is host-bound, e.g. during tracking).
     ints = torch.empty((2, P), **i32)                       # radii | n_touched
     radii, n_touched = ints[0], ints[1]
-    geom = torch.empty((_lib.g4r_geom_bytes(P),), **u8)
-    img = torch.empty((_lib.g4r_image_bytes(W, H),), **u8)
+    geom = torch.empty((_bytes("g4r_geom_bytes", P),), **u8)
+    img = torch.empty((_bytes("g4r_image_bytes", W, H),), **u8)
 
     keep: list = []
-    with torch.cuda.device(device):
+    with _on_device(device):
         ctx = _context(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         frame = _make_frame(rs, device, M, keep)
@@ -403,8 +436,8 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
 
     grad_out_color = _dev_f32(grad_out_color, device)
     grad_out_depth = _dev_f32(grad_out_depth, device)
-    scratch = torch.empty((_lib.g4r_backward_scratch_bytes(P),), dtype=torch.uint8, device=device)
-    with torch.cuda.device(device):
+    scratch = torch.empty((_bytes("g4r_backward_scratch_bytes", P),), dtype=torch.uint8, device=device)
+    with _on_device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         # the forward's frame struct (camera pointers; the tensors behind them are kept alive next to it) is reused
         frame, keep = frame_keep if frame_keep is not None else (None, [])
