@@ -603,7 +603,12 @@ def main():
                                    f"num_rendered N={N}", "parallelism": f"views x{world} (independent frames per GPU, no data-path collective)",
                        "l2": "flushed between steps (256 MiB memset outside the timed events)", "timing": "CUDA events per step on the current stream, "
                        "sum over K steps, max over ranks", "api": "public GaussianRasterizer autograd API (Python -> ctypes -> C ABI)"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes},
+            # e2e streams the frame's 28 MB of Gaussian tensors from pinned host memory every step (double-buffered on a side
+            # stream): h2d_gbs_per_gpu = what each GPU's host link sustains at this rate; once it sits at the link's practical
+            # rate (~35-50 GB/s per PCIe gen5 x16 GPU; N ranks share the host's DRAM / root complexes) e2e is copy-bound, not
+            # kernel-bound, which is what separates it from `value`.
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
+                    "h2d_gbs_per_gpu": e2e_value / world * wl.h2d_bytes / 1e9, "h2d_gbs_aggregate": e2e_value * wl.h2d_bytes / 1e9},
             # launches of this library's kernels inside the timed region, counted by the library's stage profile (it covers
             # the warm-up steps too, which run the same launches)
             "gpu_launches": int(round(sum(v[1] for v in stage.values()) * args.steps / (args.steps + args.warmup))) if stage else 0,
