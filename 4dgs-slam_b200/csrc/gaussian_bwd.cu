@@ -10,6 +10,11 @@
 // reference kernels skip: backward.cu:163,443), so the caller never pre-zeroes anything.  The
 // SE(3) pose gradient dL/dtau is reduced warp -> CTA -> 6 global atomics per CTA.
 //
+// The SH derivative sums (the DSH / dd{x,y,z} block) and dL/dq are the closed-form derivatives written term by term in the order
+// of the reference's backward.cu:48-123,404-408 -- bug-compatible gradients need the same terms; the kernel structure around
+// them (one fused kernel, write-once rows, optional outputs, in-kernel pose reduction, raw-parameter chain rule, dynamic
+// offsets) is this repo's.
+//
 // Semantics follow the reference including its approximations:
 // the pose Jacobian of the 2D mean uses proj_raw entries a, b, e only (:465-484); the
 // SH view-direction term contributes -dL/dmean to rho only (:141-143); -[t]x is built from
@@ -251,10 +256,10 @@ __global__ void __launch_bounds__(G4R_BLOCK, 4) gaussian_backward_kernel(const G
             // raw mode: coefficient 0 <-> _features_dc [P,1,3], coefficients 1.. <-> _features_rest [P,M-1,3]
             const bool split = kRaw && p.M > 1;
             const float* sh = kRaw ? p.shs + (size_t)i * 3 : p.shs + (size_t)i * p.M * 3;
-            const float* shr = split ? p.shs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : sh;
+            const float* shr = split ? p.shs_rest + ((ptrdiff_t)i * (p.M - 1) - 1) * 3 : sh;      // signed: negative shift for i == 0
             const bool want_dsh = p.dL_dshs != nullptr;      // NULL: the caller does not need dL/dSH (needs_input_grad)
             float* dsh = kRaw ? p.dL_dshs + (size_t)i * 3 : p.dL_dshs + (size_t)i * p.M * 3;
-            float* dshr = split ? p.dL_dshs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : dsh;
+            float* dshr = split ? p.dL_dshs_rest + ((ptrdiff_t)i * (p.M - 1) - 1) * 3 : dsh;
 #define SHV(k) v3(__ldg(((k) == 0 ? sh : shr) + (k) * 3), __ldg(((k) == 0 ? sh : shr) + (k) * 3 + 1), __ldg(((k) == 0 ? sh : shr) + (k) * 3 + 2))
 #define DSH(k, f) { if (want_dsh) { const float f__ = (f); float* d__ = ((k) == 0 ? dsh : dshr) + (k) * 3; d__[0] = f__ * dRGB.x; d__[1] = f__ * dRGB.y; d__[2] = f__ * dRGB.z; } }
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;    // dL/d(dir) accumulated as dot(dRGB/d(dir), dRGB)

@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(G4R_BLOCK) project_kernel(const ProjectParams 
         dx = dx / len; dy = dy / len; dz = dz / len;
         // raw mode: coefficient 0 lives in _features_dc [P,1,3], the others in _features_rest [P,M-1,3]
         const float* sh = kRaw ? p.shs + (size_t)i * 3 : p.shs + (size_t)i * p.M * 3;
-        const float* shr = (kRaw && p.M > 1) ? p.shs_rest + ((size_t)i * (p.M - 1) - 1) * 3 : sh;
+        // coefficient k >= 1 of Gaussian i sits at shs_rest[(i*(M-1) + k-1)*3]; the base is shifted by one coefficient so that the
+        // SH(k, c) macro can index with k directly (signed arithmetic: the shift is negative for i == 0)
+        const float* shr = (kRaw && p.M > 1) ? p.shs_rest + ((ptrdiff_t)i * (p.M - 1) - 1) * 3 : sh;
 #define SH(k, c) __ldg(((k) == 0 ? sh : shr) + (k) * 3 + (c))
         float col[3];
 #pragma unroll

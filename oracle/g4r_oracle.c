@@ -19,7 +19,7 @@
  *                          sum of dL_dtau over P     DGR/diff_gaussian_rasterization/__init__.py:152-154
  *
  * Parity status: PINNED against outputs of the unmodified reference build run on a B200
- * (the .npz files under tests/golden, generated by tools/make_golden.py; see tests/test_oracle_golden.py).
+ * (the .npz files under tests/golden, generated on a B200 by tools/gpu_check.py --golden; see tests/test_oracle_golden.py).
  * The reference itself ships no tests or golden vectors.
  *
  * Built twice (oracle/Makefile): REAL=float -> libg4r_oracle_f32.so (bit-faithful on the integer
