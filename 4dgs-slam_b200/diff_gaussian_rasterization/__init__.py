@@ -466,20 +466,37 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                                      theta, rho, raster_settings)
 
 
-def _debug_sync(rs, t) -> None:
-    """`debug=True` (reference __init__.py:84-99,133-150): the reference synchronises after each call so that an asynchronous
-    kernel failure surfaces at the call that caused it (and dumps its arguments to snapshot_*.dump, which is not reproduced)."""
-    if getattr(rs, "debug", False) and t.is_cuda and not torch.cuda.is_current_stream_capturing():
-        torch.cuda.synchronize(t.device)
+def _cpu_copy(args):
+    """cpu_deep_copy_tuple of the reference (__init__.py:18-20): the tensors of an argument tuple copied to the host."""
+    return tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
+
+
+def _debug_call(rs, which: str, args, fn):
+    """`debug=True`: like the reference (__init__.py:90-97,141-148), the arguments are copied to the host before the call, and if
+    the call (including the synchronisation behind it) raises they are written to snapshot_fw.dump / snapshot_bw.dump."""
+    if not getattr(rs, "debug", False) or (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+        return fn()
+    cpu_args = _cpu_copy(args)
+    try:
+        out = fn()
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                torch.cuda.synchronize(a.device)
+                break
+        return out
+    except Exception:
+        torch.save(cpu_args, f"snapshot_{which}.dump")
+        print(f"\nAn error occured in {'forward' if which == 'fw' else 'backward'}. Writing snapshot_{which}.dump for debugging.\n")
+        raise
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho,
                 raster_settings):
-        color, radii, depth, opacity, n_touched, state = _forward_impl(
-            means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
-        _debug_sync(raster_settings, means3D)
+        color, radii, depth, opacity, n_touched, state = _debug_call(
+            raster_settings, "fw", (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings),
+            lambda: _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings))
         ctx.raster_settings = raster_settings
         ctx.num_rendered = state["N"]
         ctx.P = state["P"]
@@ -500,15 +517,16 @@ class _RasterizeGaussians(torch.autograd.Function):
         needs = ctx.needs_input_grad
         want = dict(means3D=needs[0], means2D=needs[1], sh=needs[2], colors=needs[3], opacities=needs[4], scales=needs[5],
                     rotations=needs[6], cov=needs[7])
-        (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau) = _backward_impl(
-            rs, ctx.P, means3D_c,
-            _dev_f32(sh, device) if sh.numel() else sh,
-            _dev_f32(colors_precomp, device) if colors_precomp.numel() else colors_precomp,
-            _dev_f32(scales, device) if scales.numel() else scales,
-            _dev_f32(rotations, device) if rotations.numel() else rotations,
-            _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp,
-            radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep, want=want)
-        _debug_sync(rs, means3D)
+        (grad_means3D, grad_means2D, grad_sh, grad_colors, grad_opacities, grad_scales, grad_rot, grad_cov, tau) = _debug_call(
+            rs, "bw", (means3D, radii, colors_precomp, scales, rotations, cov3Ds_precomp, grad_out_color, grad_out_depth, sh, rs),
+            lambda: _backward_impl(
+                rs, ctx.P, means3D_c,
+                _dev_f32(sh, device) if sh.numel() else sh,
+                _dev_f32(colors_precomp, device) if colors_precomp.numel() else colors_precomp,
+                _dev_f32(scales, device) if scales.numel() else scales,
+                _dev_f32(rotations, device) if rotations.numel() else rotations,
+                _dev_f32(cov3Ds_precomp, device) if cov3Ds_precomp.numel() else cov3Ds_precomp,
+                radii, geom, img, binning, ctx.opacities_shape, grad_out_color, grad_out_depth, ctx.frame_keep, want=want))
         grad_rho = tau[:3].view(1, -1)
         grad_theta = tau[3:6].view(1, -1)
         return (

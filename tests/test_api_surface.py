@@ -106,3 +106,22 @@ def test_fused_rasterizer_surface_and_argument_checks():
         dgr.FusedGaussianRasterizer(rs)(**dict(args, scaling_raw=torch.zeros(P, 2)))
     with pytest.raises(RuntimeError, match="features_dc"):
         dgr.FusedGaussianRasterizer(rs)(**dict(args, features_dc=torch.zeros(P, 3)))
+
+
+def test_debug_mode_writes_the_argument_snapshot_on_failure(tmp_path, monkeypatch):
+    """debug=True: like the reference (DGR/diff_gaussian_rasterization/__init__.py:90-97) the arguments are copied to the host
+    before the call and written to snapshot_fw.dump when the call raises.  (A CPU tensor is the failure that needs no GPU.)"""
+    import pytest
+    import torch
+    import diff_gaussian_rasterization as dgr
+    monkeypatch.chdir(tmp_path)
+    eye = torch.eye(4)
+    rs = dgr.GaussianRasterizationSettings(image_height=32, image_width=32, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3), scale_modifier=1.0,
+                                           viewmatrix=eye, projmatrix=eye, projmatrix_raw=eye, sh_degree=0, campos=torch.zeros(3),
+                                           prefiltered=False, debug=True)
+    P = 5
+    with pytest.raises(RuntimeError):
+        dgr.GaussianRasterizer(rs)(means3D=torch.zeros(P, 3), means2D=torch.zeros(P, 3), opacities=torch.ones(P, 1), shs=torch.zeros(P, 1, 3),
+                                   scales=torch.ones(P, 3), rotations=torch.ones(P, 4))
+    snap = torch.load(tmp_path / "snapshot_fw.dump", weights_only=False)
+    assert isinstance(snap, tuple) and snap[0].shape == (P, 3)
