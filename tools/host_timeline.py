@@ -74,6 +74,7 @@ def main():
     native = ["g4r_forward_project", "g4r_forward_render", "g4r_wait_num_rendered", "g4r_backward", "g4r_geom_bytes",
               "g4r_image_bytes", "g4r_binning_bytes", "g4r_backward_scratch_bytes"]
     orig = {n: getattr(dgr._lib, n) for n in native}
+    py_orig = {"_forward_impl": dgr._forward_impl, "_backward_impl": dgr._backward_impl}      # this package's Python between autograd and the C ABI
     out = {}
     for name, sc_cpu in cases.items():
         sc = sc_cpu.to(dev)
@@ -83,9 +84,13 @@ def main():
             acc = {}
             for n in native:
                 setattr(dgr._lib, n, Timed(orig[n], n, acc))
+            for n, f in py_orig.items():
+                setattr(dgr, n, (lambda f_, n_: (lambda *a, **k: Timed(lambda: f_(*a, **k), n_, acc)()))(f, n))
             wall, h = loop(sc, dgr, 50, fresh)
             for n in native:
                 setattr(dgr._lib, n, orig[n])
+            for n, f in py_orig.items():
+                setattr(dgr, n, f)
             tag = "fresh_leaves" if fresh else "reused_leaves"
             row[tag] = {"wall_ms": round(wall, 4), "host_setup_ms": round(h[0], 4), "host_forward_ms": round(h[1], 4),
                         "host_loss_ms": round(h[2], 4), "host_backward_ms": round(h[3], 4),
