@@ -324,6 +324,16 @@ typedef struct G4RLossIn {
 } G4RLossIn;
 int g4r_slam_loss(const G4RLossIn* in, float* dL_dimage, float* dL_ddepth, float* out4, void* scratch32, void* stream);
 
+/* ---- simple-knn distCUDA2 ----------------------------------------------------------------------
+ * Replaces SimpleKNN::knn (submodules/simple-knn/simple_knn.cu:185-220) behind distCUDA2 (spatial.cu:15-26): mean_dist2[i] = mean
+ * of the squared distances from points[i] to its 3 nearest other points (FLT_MAX stands in for a missing neighbour when P < 4,
+ * giving FLT_MAX / 3 or +inf like the reference).  points = [P,3] float32, mean_dist2 = [P] float32, both DEVICE pointers;
+ * scratch = g4r_knn_scratch_bytes(P) bytes of device memory owned by the caller.  Enqueued on `stream`, no host synchronisation
+ * and no allocation (the reference allocates, frees and copies the bounding box to the host twice per call).  Bit-identical to
+ * the reference build's output. */
+size_t g4r_knn_scratch_bytes(int32_t P);
+int g4r_knn_mean_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------- */
 int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);

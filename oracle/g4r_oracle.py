@@ -20,13 +20,27 @@ _BUILD = os.path.join(_HERE, "_build")
 
 
 def build(force: bool = False) -> None:
-    """Compile both oracle libraries with the committed Makefile (gcc, -ffp-contract=off)."""
-    need = force or not all(os.path.exists(os.path.join(_BUILD, f"libg4r_oracle_{p}.so")) for p in ("f32", "f64"))
-    src = os.path.join(_HERE, "g4r_oracle.c")
+    """Compile the oracle libraries with the committed Makefile (gcc, -ffp-contract=off)."""
+    libs = ("libg4r_oracle_f32.so", "libg4r_oracle_f64.so", "libknn_oracle.so", "libknn_search_host.so")
+    srcs = [os.path.join(_HERE, "g4r_oracle.c"), os.path.join(_HERE, "knn_oracle.c"),
+            os.path.join(_HERE, "..", "tests", "native", "knn_search_host.cpp"),
+            os.path.join(_HERE, "..", "4dgs-slam_b200", "csrc", "knn_search.cuh")]
+    need = force or not all(os.path.exists(os.path.join(_BUILD, f)) for f in libs)
     if not need:
-        need = any(os.path.getmtime(os.path.join(_BUILD, f"libg4r_oracle_{p}.so")) < os.path.getmtime(src) for p in ("f32", "f64"))
+        newest = max(os.path.getmtime(s) for s in srcs)
+        need = any(os.path.getmtime(os.path.join(_BUILD, f)) < newest for f in libs)
     if need:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, stdout=subprocess.DEVNULL)
+
+
+def knn_mean_dist2(points: np.ndarray) -> np.ndarray:
+    """distCUDA2 restated as a brute force (oracle/knn_oracle.c): float32 [P] from float32 [P,3]."""
+    build()
+    lib = ctypes.CDLL(os.path.join(_BUILD, "libknn_oracle.so"))
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    out = np.empty(pts.shape[0], np.float32)
+    lib.knn_oracle_mean_dist2(ctypes.c_int32(pts.shape[0]), ctypes.c_void_p(pts.ctypes.data), ctypes.c_void_p(out.ctypes.data))
+    return out
 
 
 def _scene_struct(real):

@@ -1,0 +1,126 @@
+"""distCUDA2 (simple-knn): mean squared distance to the 3 nearest neighbours.
+
+Chain of evidence: the UNMODIFIED reference build ran on the bit-reproducible clouds of tools/knn_cases.py on a B200 and its
+outputs were recorded as sha256 digests (tests/golden/knn_digests_ref.json, tools/knn_digests.py).  On CPU the brute-force
+restatement (oracle/knn_oracle.c) and the host build of the product's search code (csrc/knn_search.cuh) are pinned to those
+digests and to each other on clouds that stress the search; on the GPU the CUDA path must reproduce the digests, the oracle
+and -- when baseline/_ref travelled to the box -- the reference build itself, bit for bit."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import g4r_oracle
+from tools import knn_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "tests", "golden", "knn_digests_ref.json")
+REF = json.load(open(PATH)) if os.path.exists(PATH) else {}
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_digest_file_covers_every_cloud():
+    assert list(REF) == list(knn_cases.EXACT_CLOUDS), "run tools/knn_digests.py --write on a GPU box that has baseline/_ref"
+
+
+@pytest.mark.parametrize("name", list(knn_cases.EXACT_CLOUDS))
+def test_exact_clouds_are_bit_reproducible(name):
+    if name not in REF:
+        pytest.skip("no digest")
+    assert knn_cases.sha(knn_cases.exact_cloud(name)) == REF[name]["input_sha256"]
+
+
+def test_oracle_matches_the_reference_digest():
+    """The brute force on K1 (20 k points) == the reference build's output, bit for bit."""
+    name = "K1_depthmap_20k"
+    if name not in REF:
+        pytest.skip("no digest")
+    assert knn_cases.sha(g4r_oracle.knn_mean_dist2(knn_cases.exact_cloud(name))) == REF[name]["sha256"]
+
+
+@pytest.mark.parametrize("name", list(knn_cases.EXACT_CLOUDS))
+def test_host_build_of_the_search_matches_the_reference_digests(name):
+    """The product's search code compiled for the host reproduces the reference output at every size up to 2 M points."""
+    if name not in REF:
+        pytest.skip("no digest")
+    out, stats = knn_cases.host_search(knn_cases.exact_cloud(name))
+    assert knn_cases.sha(out) == REF[name]["sha256"]
+    assert stats["evals_per_query"] < 400 and stats["rounds_per_query"] < 1.5, stats       # the search stays local
+
+
+def test_host_build_of_the_search_equals_the_oracle_on_hard_clouds():
+    for name, pts in knn_cases.random_cases(seed=1, n=6000):
+        want = g4r_oracle.knn_mean_dist2(pts)
+        got, _ = knn_cases.host_search(pts)
+        assert np.array_equal(bits(got), bits(want)), name
+
+
+def test_oracle_semantics_on_tiny_inputs():
+    """P < 4: missing neighbours count as FLT_MAX (simple_knn.cu:153): one missing -> FLT_MAX / 3, two or three -> the float sum
+    overflows to +inf; P = 4: plain mean."""
+    pts = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3]], np.float32)
+    np.testing.assert_array_equal(g4r_oracle.knn_mean_dist2(pts), np.array([14 / 3, 16 / 3, 22 / 3, 32 / 3], np.float32))
+    np.testing.assert_array_equal(g4r_oracle.knn_mean_dist2(pts[:3]), np.full(3, np.finfo(np.float32).max / np.float32(3), np.float32))
+    assert np.isinf(g4r_oracle.knn_mean_dist2(pts[:2])).all()
+    assert np.isinf(g4r_oracle.knn_mean_dist2(pts[:1])).all()
+
+
+def test_distCUDA2_has_no_cpu_path():
+    from simple_knn._C import distCUDA2
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        distCUDA2(torch.zeros(8, 3))
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(knn_cases.EXACT_CLOUDS))
+def test_cuda_matches_the_reference_digests(device, name):
+    from simple_knn._C import distCUDA2
+    if name not in REF:
+        pytest.skip("no digest")
+    out = distCUDA2(torch.from_numpy(knn_cases.exact_cloud(name)).to(device))
+    assert knn_cases.sha(out.cpu().numpy()) == REF[name]["sha256"]
+
+
+@pytest.mark.gpu
+def test_cuda_equals_the_oracle_on_hard_clouds(device):
+    from simple_knn._C import distCUDA2
+    for name, pts in knn_cases.random_cases(seed=2, n=12000):
+        want = g4r_oracle.knn_mean_dist2(pts)
+        got = distCUDA2(torch.from_numpy(pts).to(device)).cpu().numpy()
+        assert got.dtype == np.float32 and got.shape == (pts.shape[0],)
+        assert np.array_equal(bits(got), bits(want)), name
+
+
+@pytest.mark.gpu
+def test_cuda_equals_the_reference_build_when_present(device):
+    """baseline/_ref/simple_knn (the unmodified reference, built for sm_100a) on the same box: bit-identical."""
+    from simple_knn._C import distCUDA2
+    from tools.knn_digests import load_reference
+    ref = load_reference()
+    if ref is None:
+        pytest.skip("baseline/_ref/simple_knn not on this box")
+    for name, pts in list(knn_cases.random_cases(seed=3, n=50000)) + [("K3", knn_cases.exact_cloud("K3_depthmap_500k"))]:
+        if pts.shape[0] < 4:
+            continue
+        t = torch.from_numpy(pts).to(device)
+        assert torch.equal(distCUDA2(t).view(torch.int32), ref.distCUDA2(t).view(torch.int32)), name
+
+
+@pytest.mark.gpu
+def test_distCUDA2_surface(device):
+    """Shapes / dtypes / edge cases of the reference entry point (spatial.cu:15-26): [P,3] float -> [P] float32; P = 0 is
+    empty; non-contiguous and float64 input is accepted; the caller's clamp_min + log (gaussian_model.py:381-382) works."""
+    from simple_knn._C import distCUDA2
+    assert distCUDA2(torch.zeros(0, 3, device=device)).shape == (0,)
+    pts = torch.rand(1000, 3, device=device)
+    a = distCUDA2(pts)
+    assert torch.equal(a, distCUDA2(pts.double())) and torch.equal(a, distCUDA2(pts.t().contiguous().t()))
+    assert torch.isfinite(torch.log(torch.sqrt(torch.clamp_min(a, 1e-7)))).all()
+    with pytest.raises(RuntimeError):
+        distCUDA2(torch.zeros(5, 2, device=device))

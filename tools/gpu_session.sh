@@ -46,6 +46,10 @@ for stage in "$@"; do
     determinism) timeout 900 python tools/determinism_check.py > gpurun_out/determinism.log 2>&1; echo "rc=$?"; cut -c1-2500 gpurun_out/determinism.log ;;
     repro)    timeout 900 python tools/repro_anomaly.py 16 > gpurun_out/repro_anomaly.log 2>&1; echo "rc=$?"; cut -c1-1500 gpurun_out/repro_anomaly.log ;;
     prelude)  timeout 600 python tools/prelude_bench.py > gpurun_out/prelude_bench.log 2>&1; echo "rc=$?"; cut -c1-700 gpurun_out/prelude_bench.log ;;
+    knn)      timeout 900 python tools/knn_digests.py --write gpurun_out/knn_digests_ref.json > gpurun_out/knn_digests.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/knn_digests.log | cut -c1-400
+              [ -f gpurun_out/knn_digests_ref.json ] && [ ! -f tests/golden/knn_digests_ref.json ] && cp gpurun_out/knn_digests_ref.json tests/golden/
+              timeout 900 python -m pytest tests/test_knn.py -m gpu -q --timeout 600 > gpurun_out/pytest_knn.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_knn.log ;;
+    knnsan)   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/knn_digests.py K1_depthmap_20k K5_duplicates_60k > gpurun_out/knn_memcheck.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/knn_memcheck.log ;;
     digests)  timeout 900 python tools/digests.py --write gpurun_out/digests_ref.json > gpurun_out/digests.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/digests.log ;;
     shapes)   for wl in C3map track; do for impl in ours reference; do
                 timeout 600 python bench.py --workload $wl --impl $impl --steps 100 > gpurun_out/bench_${wl}_${impl}.json 2> gpurun_out/bench_${wl}_${impl}.err; echo "$wl $impl rc=$?"; cut -c1-600 gpurun_out/bench_${wl}_${impl}.json; tail -3 gpurun_out/bench_${wl}_${impl}.err
