@@ -10,11 +10,14 @@
 // What this does instead: 63-bit Morton codes (21 bits per axis) over the cubic bounding box, sorted once.  Every octree cell of
 // every level is then one contiguous range of the sorted list (a prefix of the code), found through a dense table for the first
 // KnnIndex::T levels and a short binary search inside the table range below that.  A query
-//   1. picks the finest level at which its own cell holds >= 4 points (common prefix with its sorted neighbours j-3 .. j+3),
-//   2. scans the 3x3x3 block of cells around it at that level (own cell first, the others pruned by box distance),
-//   3. is done when its third-best distance is no larger than the distance to the nearest face of the block that has cells behind
-//      it; otherwise it repeats one level up (at most twice in practice, because the own cell already holds 3 neighbours).
-// The work per query is a few hundred distance evaluations whatever the density, instead of P/1024 box tests + thousands of
+//   1. takes the third-best distance among its Morton neighbours j-3 .. j+3 as an upper bound r^2 (the reference's first loop),
+//   2. picks the level whose cells are just wider than r, so that the 3x3x3 block of cells around it contains the ball of radius r,
+//   3. visits the block (own cell first; every cell pruned by its box distance against min(r^2, third best so far)); a cell that
+//      holds more than KNN_LEAF points is opened instead of scanned -- a stackless nearest-first walk over its sub-cells, each
+//      pruned the same way -- so a sparse query next to a dense region does not pay for the region,
+//   4. is done when its third-best distance is no larger than the distance to the nearest face of the block that has cells behind
+//      it (always true after one round up to rounding; otherwise it repeats one level up).
+// The work per query is a few dozen distance evaluations whatever the density, instead of P/1024 box tests + thousands of
 // evaluations, and it does not degrade when a few far outliers blow up the bounding box (the level is chosen per query).
 // Results are bit-identical to the reference: same distance arithmetic, and the set of three smallest values does not depend on the
 // visiting order.
@@ -31,6 +34,7 @@
 
 #define KNN_BITS 21            // bits per axis of the Morton code
 #define KNN_LMAX 19            // finest level a query may start at (cells of 4 code units: the 1-unit rounding margin stays < 25 %)
+#define KNN_LEAF 32            // a cell with more points than this is opened (its children pruned one by one), not scanned
 #define KNN_MARGIN 1.0f        // bound on the error of a difference of two computed cell coordinates, in code units (see knn_cell)
 
 struct alignas(16) KnnPoint { float x, y, z; uint32_t idx; };   // 16 bytes (one 128-bit load): position + original index, in Morton order
@@ -86,6 +90,16 @@ KNN_HD uint64_t knn_expand21(uint32_t v) {
     x = (x | x << 2) & 0x1249249249249249ull;
     return x;
 }
+// inverse: every third bit of 63 -> 21 bits
+KNN_HD uint32_t knn_compact21(uint64_t x) {
+    x &= 0x1249249249249249ull;
+    x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ull;
+    x = (x ^ (x >> 4)) & 0x100f00f00f00f00full;
+    x = (x ^ (x >> 8)) & 0x1f0000ff0000ffull;
+    x = (x ^ (x >> 16)) & 0x1f00000000ffffull;
+    x = (x ^ (x >> 32)) & 0x1fffffull;
+    return (uint32_t)x;
+}
 KNN_HD uint64_t knn_morton(uint32_t cx, uint32_t cy, uint32_t cz) { return knn_expand21(cx) | (knn_expand21(cy) << 1) | (knn_expand21(cz) << 2); }
 
 KNN_HD KnnGrid knn_make_grid(float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
@@ -140,9 +154,9 @@ KNN_HD void knn_range(const KnnIndex& ix, int level, uint64_t key, uint32_t* lo,
     }
 }
 
-// finest level (<= KNN_LMAX) at which the cell of sorted position j holds at least 4 points
-KNN_HD int knn_start_level(const KnnIndex& ix, int j) {
-    int level = 0;
+// finest level at which the cell of sorted position j holds at least 4 points (common prefix with the sorted neighbours)
+KNN_HD int knn_window_level(const KnnIndex& ix, int j) {
+    int level = -1;
     const uint64_t* c = ix.code;
     for (int a = j - 3; a <= j; ++a) {
         const int b = a + 3;
@@ -152,71 +166,189 @@ KNN_HD int knn_start_level(const KnnIndex& ix, int j) {
         const int l = common / 3;
         if (l > level) level = l;
     }
-    return level < KNN_LMAX ? level : KNN_LMAX;
+    return level;                                              // -1: fewer than 4 points in total
 }
 
-struct KnnStats { uint32_t evals, cells, rounds; };            // host-side instrumentation (tests); the device passes nullptr
+// level whose cells are at least as wide as the ball of squared radius r2: the 3x3x3 block around the query then contains the
+// ball.  KNN_LMAX bounds it from below (dense spots: the cells are opened, not scanned).
+KNN_HD int knn_level_for(const KnnGrid& g, float r2) {
+    if (!(g.unit > 0.0f) || !(r2 < FLT_MAX)) return 0;
+    const float r_units = sqrtf(r2) / g.unit * 1.0001f + 2.0f * KNN_MARGIN + 1.0f;
+    if (!(r_units < 2097152.0f)) return 0;
+    const uint32_t need = (uint32_t)r_units + 1u;              // cell side in code units, rounded up ...
+    int shift = 0;
+    while ((1u << shift) < need) ++shift;                      // ... to a power of two
+    const int level = KNN_BITS - shift;
+    return level > KNN_LMAX ? KNN_LMAX : (level < 0 ? 0 : level);
+}
+
+KNN_HD float knn_dist2(const KnnPoint& p, const KnnPoint& q) {
+    const float dx = knn_sub(p.x, q.x), dy = knn_sub(p.y, q.y), dz = knn_sub(p.z, q.z);
+    return knn_fma(dz, dz, knn_fma(dx, dx, knn_mul(dy, dy)));          // nvcc's contraction of simple_knn.cu:134 (FMUL on y, FFMA x, FFMA z)
+}
+
+struct KnnStats { uint32_t evals, cells, rounds, nodes; };     // host-side instrumentation (tests); the device passes nullptr
+
+struct KnnQuery {
+    KnnPoint q;
+    float u[3];              // position in code units
+    float best[3];
+    float reject;            // third-best distance among the Morton neighbours j-3 .. j+3: an upper bound of the answer (simple_knn.cu:153-161)
+    float unit2;
+};
+
+// squared distance (code units, shrunk by the rounding margin per axis) from the query to the cell `key` of `level`
+KNN_HD float knn_box_dist2(const KnnQuery& Q, int level, uint64_t key) {
+    const float S = (float)(1u << (KNN_BITS - level));
+    float bd2 = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+        const float lo = (float)knn_compact21(key >> a) * S;
+        float d = fmaxf(lo - Q.u[a], Q.u[a] - (lo + S));
+        d = fmaxf(d - KNN_MARGIN, 0.0f);
+        bd2 += d * d;
+    }
+    return bd2;
+}
+
+KNN_HD void knn_scan(const KnnIndex& ix, KnnQuery& Q, uint32_t lo, uint32_t hi, KnnStats* st) {
+    for (uint32_t i = lo; i < hi; ++i) {
+        const KnnPoint p = ix.pts[i];
+        if (p.idx == Q.q.idx) continue;                         // simple_knn.cu:156,174: only the query itself is skipped
+        knn_insert(Q.best, knn_dist2(p, Q.q));
+        if (st) st->evals++;
+        if (Q.best[2] == 0.0f) return;                          // three coincident points: nothing can improve
+    }
+}
+
+// child of the cell (level, key) that is nearest to the query: per axis, the half the query's coordinate falls into (or faces)
+KNN_HD uint32_t knn_octant(const KnnQuery& Q, int level, uint64_t key) {
+    const float Sc = (float)(1u << (KNN_BITS - level - 1));     // child side
+    uint32_t oct = 0;
+    for (int a = 0; a < 3; ++a) {
+        const float centre = (float)(2u * knn_compact21(key >> a) + 1u) * Sc;
+        if (Q.u[a] >= centre) oct |= 1u << a;
+    }
+    return oct;
+}
+
+// Everything in the cell (level0, key0) = sorted range [rlo, rhi) that can still improve the answer.  A cell with more than
+// KNN_LEAF points is not scanned but opened: its 8 children are visited nearest first (child index v ^ octant of the query,
+// v = 0 .. 7), each pruned by its box distance, so the bound tightens before the far children are looked at.  The traversal needs
+// no stack: `vkey` holds the visit counters v of the path (3 bits per level) next to the real Morton key, the next node is the
+// next counter value at this level or, when it wraps, at the parent's.  A sub-cell's range comes from the prefix table
+// (levels <= T) or a binary search inside its T-level ancestor (or inside the root, when the root is deeper than T).
+KNN_HD void knn_visit(const KnnIndex& ix, KnnQuery& Q, int level0, uint64_t key0, uint32_t rlo, uint32_t rhi, KnnStats* st) {
+    int level = level0;
+    uint64_t key = key0, vkey = 0;
+    for (;;) {
+        bool descend = false;
+        if (st) st->nodes++;
+        if (level == level0 || !(knn_box_dist2(Q, level, key) * Q.unit2 * 0.99999f > fminf(Q.best[2], Q.reject))) {
+            uint32_t lo = rlo, hi = rhi;
+            if (level != level0) {
+                if (level <= ix.T || level0 < ix.T) knn_range(ix, level, key, &lo, &hi);     // table, or search inside the T-level ancestor
+                else {                                                                        // the root is the tighter bracket
+                    const int sh = 63 - 3 * level;
+                    lo = knn_lower_bound(ix.code, rlo, rhi, key << sh);
+                    hi = knn_lower_bound(ix.code, lo, rhi, (key + 1) << sh);
+                }
+            }
+            if (hi - lo > KNN_LEAF && level < KNN_BITS) descend = true;
+            else knn_scan(ix, Q, lo, hi, st);
+        }
+        if (Q.best[2] == 0.0f) return;
+        if (descend) {
+            key = (key << 3) | knn_octant(Q, level, key);
+            vkey <<= 3;
+            ++level;
+            continue;
+        }
+        for (;;) {                                              // next node: nearest-first order among siblings, then up
+            if (level == level0) return;
+            const uint32_t v = (uint32_t)(vkey & 7u) + 1u;
+            if (v < 8u) {
+                const uint64_t parent = key >> 3;
+                key = (parent << 3) | (v ^ knn_octant(Q, level - 1, parent));
+                vkey = (vkey & ~7ull) | v;
+                break;
+            }
+            key >>= 3;
+            vkey >>= 3;
+            --level;
+        }
+    }
+}
 
 KNN_HD float knn_query(const KnnIndex& ix, const KnnGrid& g, int j, KnnStats* st) {
-    const KnnPoint q = ix.pts[j];
-    float u[3];
+    KnnQuery Q;
+    Q.q = ix.pts[j];
     uint32_t c0[3];
-    knn_cell(g, q.x, q.y, q.z, u, c0);
-    int level = knn_start_level(ix, j);
-    float best[3];
-    const float unit2 = g.unit * g.unit;
+    knn_cell(g, Q.q.x, Q.q.y, Q.q.z, Q.u, c0);
+    Q.unit2 = g.unit * g.unit;
+    float start2;            // squared radius the first round is sized for
+    {   // upper bound from the neighbours in Morton order, like the reference's first loop
+        float r[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+        const int a = j - 3 < 0 ? 0 : j - 3, b = j + 3 > ix.P - 1 ? ix.P - 1 : j + 3;
+        for (int i = a; i <= b; ++i) {
+            if (i != j) knn_insert(r, knn_dist2(ix.pts[i], Q.q));
+        }
+        Q.reject = r[2];
+        // second bound: 4 points share the query's cell at the window level, so three of them are within its diagonal
+        const int wl = knn_window_level(ix, j);
+        if (wl >= 0) {
+            const float side = ((float)(1u << (KNN_BITS - wl)) + KNN_MARGIN) * g.unit;
+            Q.reject = fminf(Q.reject, 3.0f * side * side * 1.00001f);
+        }
+        // Where the Morton curve jumps (cell corners), the third neighbour along the curve can be far away although the real
+        // neighbours sit just across the cell face: then both bounds are useless (measured: 3.5 k cells opened for one query).
+        // The nearest curve neighbour is usually still a real neighbour, so the first round is sized for 4x its distance; a
+        // round that does not settle the query tightens the bound and the next one is sized from it.
+        const float d1 = r[0] > 0.0f ? r[0] : (r[1] > 0.0f ? r[1] : r[2]);
+        start2 = fminf(Q.reject, 16.0f * d1);
+    }
+    int level = knn_level_for(g, start2);
     for (;;) {
         const int shift = KNN_BITS - level;
         const float S = (float)(1u << shift);                  // cell side in code units
         const int G = 1 << level;
         int ck[3];
-        float lo_d[3], hi_d[3];                                // distance (code units) from the query to the low / high face of its cell
         float m = FLT_MAX;                                     // distance to the nearest block face that has cells behind it
         for (int a = 0; a < 3; ++a) {
             ck[a] = (int)(c0[a] >> shift);
-            lo_d[a] = u[a] - (float)ck[a] * S;
-            hi_d[a] = (float)(ck[a] + 1) * S - u[a];
-            if (ck[a] >= 2) m = fminf(m, lo_d[a] + S);
-            if (ck[a] + 2 <= G - 1) m = fminf(m, hi_d[a] + S);
+            const float lo_d = Q.u[a] - (float)ck[a] * S, hi_d = (float)(ck[a] + 1) * S - Q.u[a];
+            if (ck[a] >= 2) m = fminf(m, lo_d + S);
+            if (ck[a] + 2 <= G - 1) m = fminf(m, hi_d + S);
         }
-        best[0] = best[1] = best[2] = FLT_MAX;
+        Q.best[0] = Q.best[1] = Q.best[2] = FLT_MAX;
         if (st) st->rounds++;
         for (int t = 0; t < 27; ++t) {                          // offsets in the order 0, -1, +1 per axis: own cell first
-            const int o[3] = {(t % 3 == 0) ? 0 : (t % 3 == 1 ? -1 : 1), ((t / 3) % 3 == 0) ? 0 : ((t / 3) % 3 == 1 ? -1 : 1),
-                              (t / 9 == 0) ? 0 : (t / 9 == 1 ? -1 : 1)};
-            const int nx = ck[0] + o[0], ny = ck[1] + o[1], nz = ck[2] + o[2];
+            const int ox = (t % 3 == 0) ? 0 : (t % 3 == 1 ? -1 : 1), oy = ((t / 3) % 3 == 0) ? 0 : ((t / 3) % 3 == 1 ? -1 : 1),
+                      oz = (t / 9 == 0) ? 0 : (t / 9 == 1 ? -1 : 1);
+            const int nx = ck[0] + ox, ny = ck[1] + oy, nz = ck[2] + oz;
             if (nx < 0 || ny < 0 || nz < 0 || nx >= G || ny >= G || nz >= G) continue;
-            if (t > 0) {                                        // box distance, shrunk by the rounding margin per axis
-                float bd2 = 0.0f;
-                for (int a = 0; a < 3; ++a) {
-                    float d = o[a] == 0 ? 0.0f : (o[a] < 0 ? lo_d[a] : hi_d[a]);
-                    d = fmaxf(d - KNN_MARGIN, 0.0f);
-                    bd2 += d * d;
-                }
-                if (bd2 * unit2 * 0.99999f > best[2]) continue;
-            }
+            const uint64_t key = knn_morton((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+            if (t > 0 && knn_box_dist2(Q, level, key) * Q.unit2 * 0.99999f > fminf(Q.best[2], Q.reject)) continue;
             uint32_t lo, hi;
-            knn_range(ix, level, knn_morton((uint32_t)nx, (uint32_t)ny, (uint32_t)nz), &lo, &hi);
+            knn_range(ix, level, key, &lo, &hi);
             if (st) st->cells++;
-            for (uint32_t i = lo; i < hi; ++i) {
-                const KnnPoint p = ix.pts[i];
-                if (p.idx == q.idx) continue;                   // simple_knn.cu:156,174: only the query itself is skipped
-                const float dx = knn_sub(p.x, q.x), dy = knn_sub(p.y, q.y), dz = knn_sub(p.z, q.z);
-                const float d = knn_fma(dz, dz, knn_fma(dx, dx, knn_mul(dy, dy)));   // nvcc's contraction of simple_knn.cu:134
-                knn_insert(best, d);
-                if (st) st->evals++;
-                if (best[2] == 0.0f) break;                     // three coincident points: nothing can improve
-            }
-            if (best[2] == 0.0f) break;
+            if (lo == hi) continue;
+            knn_visit(ix, Q, level, key, lo, hi, st);
+            if (Q.best[2] == 0.0f) break;
         }
-        if (m == FLT_MAX || level == 0 || best[2] == 0.0f) break;   // the block covered everything there is
-        const float lb = (m - KNN_MARGIN) * g.unit * 0.999999f;     // every point outside the block is at least this far
-        if (lb > 0.0f && best[2] <= lb * lb) break;
-        --level;
+        if (m == FLT_MAX || level == 0 || Q.best[2] == 0.0f) break;   // the block covered everything there is
+        const float lb = (m - KNN_MARGIN) * g.unit * 0.999999f;       // every point outside the block is at least this far
+        if (lb > 0.0f && Q.best[2] <= lb * lb) break;
+        if (Q.best[2] < FLT_MAX) {                              // three real points seen: a valid (and now tight) bound
+            Q.reject = fminf(Q.reject, Q.best[2]);
+            const int l2 = knn_level_for(g, Q.reject);
+            level = l2 < level - 1 ? l2 : level - 1;
+        } else {
+            level = level > 2 ? level - 2 : 0;
+        }
     }
 #if defined(__CUDA_ARCH__)
-    return __fdiv_rn(__fadd_rn(__fadd_rn(best[0], best[1]), best[2]), 3.0f);
+    return __fdiv_rn(__fadd_rn(__fadd_rn(Q.best[0], Q.best[1]), Q.best[2]), 3.0f);
 #else
-    return ((best[0] + best[1]) + best[2]) / 3.0f;
+    return ((Q.best[0] + Q.best[1]) + Q.best[2]) / 3.0f;
 #endif
 }

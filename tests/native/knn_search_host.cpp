@@ -9,7 +9,7 @@
 
 #include "knn_search.cuh"
 
-extern "C" int knn_host_mean_dist2(int32_t P, const float* pts, float* out, uint64_t* stats3) {
+extern "C" int knn_host_mean_dist2(int32_t P, const float* pts, float* out, uint64_t* stats4, uint32_t* evals_per_query) {
     if (P <= 0) return 0;
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = 0; i < P; ++i)
@@ -38,13 +38,14 @@ extern "C" int knn_host_mean_dist2(int32_t P, const float* pts, float* out, uint
     for (uint32_t t = 0; t <= (1u << (3 * T)); ++t)     // the same table as knn_table_kernel
         table[t] = knn_lower_bound(scode.data(), 0u, (uint32_t)P, (uint64_t)t << sh);
     KnnIndex ix{scode.data(), sorted.data(), table.data(), P, T};
-    KnnStats st{0, 0, 0};
-    uint64_t tot[3] = {0, 0, 0};
+    KnnStats st{0, 0, 0, 0};
+    uint64_t tot[4] = {0, 0, 0, 0};
     for (int j = 0; j < P; ++j) {
-        st = KnnStats{0, 0, 0};
+        st = KnnStats{0, 0, 0, 0};
         out[sorted[j].idx] = knn_query(ix, g, j, &st);
-        tot[0] += st.evals; tot[1] += st.cells; tot[2] += st.rounds;
+        if (evals_per_query) { evals_per_query[2 * (size_t)sorted[j].idx] = st.evals; evals_per_query[2 * (size_t)sorted[j].idx + 1] = st.nodes; }
+        tot[0] += st.evals; tot[1] += st.cells; tot[2] += st.rounds; tot[3] += st.nodes;
     }
-    if (stats3) std::memcpy(stats3, tot, sizeof(tot));
+    if (stats4) std::memcpy(stats4, tot, sizeof(tot));
     return 0;
 }

@@ -83,15 +83,16 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def host_search(points: np.ndarray):
+def host_search(points: np.ndarray, per_query: bool = False):
     """The product's search code (csrc/knn_search.cuh) compiled for the HOST (tests/native/knn_search_host.cpp): test harness."""
     from oracle import g4r_oracle
     g4r_oracle.build()
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libknn_search_host.so"))
     pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
     out = np.empty(pts.shape[0], np.float32)
-    stats = np.zeros(3, np.uint64)
+    stats = np.zeros(4, np.uint64)
+    evals = np.zeros((pts.shape[0] if per_query else 0, 2), np.uint32)      # per query: distance evaluations, nodes visited
     lib.knn_host_mean_dist2(ctypes.c_int32(pts.shape[0]), ctypes.c_void_p(pts.ctypes.data), ctypes.c_void_p(out.ctypes.data),
-                            ctypes.c_void_p(stats.ctypes.data))
-    return out, dict(evals_per_query=float(stats[0]) / max(1, pts.shape[0]), cells_per_query=float(stats[1]) / max(1, pts.shape[0]),
-                     rounds_per_query=float(stats[2]) / max(1, pts.shape[0]))
+                            ctypes.c_void_p(stats.ctypes.data), ctypes.c_void_p(evals.ctypes.data if per_query else None))
+    return out, dict(evals=evals if per_query else None, evals_per_query=float(stats[0]) / max(1, pts.shape[0]), cells_per_query=float(stats[1]) / max(1, pts.shape[0]),
+                     rounds_per_query=float(stats[2]) / max(1, pts.shape[0]), nodes_per_query=float(stats[3]) / max(1, pts.shape[0]))
