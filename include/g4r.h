@@ -334,6 +334,36 @@ int g4r_slam_loss(const G4RLossIn* in, float* dL_dimage, float* dL_ddepth, float
 size_t g4r_knn_scratch_bytes(int32_t P);
 int g4r_knn_mean_dist2(int32_t P, const float* points, float* mean_dist2, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- control-node warp of the deformation step (opt-in) ------------------------------------------
+ * ControlNodeWarp.forward (utils/time_utils.py:1192-1275) after the node MLP, with cal_nn_weight (:981-1015): K nearest control
+ * nodes per Gaussian (replaces pytorch3d.ops.knn_points, :998), Gaussian-kernel weights from exp(log_radius) and
+ * sigmoid(weight_logit), blended translation (optionally in the nodes' local frames, :1208-1214), rotation and scale residuals,
+ * times motion_mask.  x [N,3] and nodes [M,node_stride] (first 3 columns = position) are constants for autograd like in the
+ * reference (:1196, :994).  Forward also writes the neighbour lists nn_idx / nn_dist (squared) / nn_weight [N,K], which the
+ * backward reads.  Backward writes the gradients of the node tensors (any output may be NULL); scratch =
+ * g4r_warp_scratch_bytes(M) bytes.  1 <= K <= 8. */
+typedef struct G4RWarpIn {
+    int32_t N, M, K;
+    int32_t node_stride;          /* floats per row of `nodes` (3 + hyper_dim) */
+    int32_t d_rot_as_res;         /* 1: rotation = sum w rot * mask (:1252); 0: ((sum w (rot + (1,0,0,0))) - (1,0,0,0)) * mask + (1,0,0,0) (:1232) */
+    int32_t local_frame;          /* 1: translate through the nodes' local rotations (:1208-1214); 0: sum w d_xyz (:1216) */
+    const float* x;               /* [N,3] */
+    const float* nodes;           /* [M,node_stride] */
+    const float* log_radius;      /* [M]   _node_radius (node_radius = exp, :893) */
+    const float* weight_logit;    /* [M]   _node_weight (node_weight = sigmoid, :897) or NULL (with_node_weight off) */
+    const float* d_xyz;           /* [M,3] node MLP outputs */
+    const float* d_rotation;      /* [M,4] */
+    const float* d_scaling;       /* [M,3] */
+    const float* local_rotation;  /* [M,4] or NULL when local_frame == 0 */
+    const float* motion_mask;     /* [N] or NULL (= 1) */
+} G4RWarpIn;
+int g4r_warp_forward(const G4RWarpIn* in, float* translate, float* rotation, float* scale, int32_t* nn_idx, float* nn_dist, float* nn_weight,
+                     void* stream);
+size_t g4r_warp_scratch_bytes(int32_t M);
+int g4r_warp_backward(const G4RWarpIn* in, const int32_t* nn_idx, const float* nn_dist, const float* nn_weight, const float* dL_dtranslate,
+                      const float* dL_drotation, const float* dL_dscale, float* dL_dd_xyz, float* dL_dd_rotation, float* dL_dd_scaling,
+                      float* dL_dlocal_rotation, float* dL_dlog_radius, float* dL_dweight_logit, void* scratch, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------- */
 int g4r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);

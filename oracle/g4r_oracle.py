@@ -271,3 +271,51 @@ def prelude_ref(xyz, scaling_act, rotation_act, dygs, dx=None, ds=None, dr=None,
         rot[dy] += np.asarray(dr)
     keep = np.arange(xyz.shape[0]) if mask is None else np.nonzero(np.asarray(mask).astype(bool))[0]
     return dict(means3D=xyz[keep], scales=sc[keep], rotations=rot[keep], keep=keep)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# control-node warp of the deformation step: torch restatement (CPU, any dtype, autograd gives the
+# gradients) of ControlNodeWarp.forward, utils/time_utils.py:1192-1275, with cal_nn_weight :981-1015 and quaternion_to_matrix
+# :115-132.  PARITY UNPINNED against the reference itself: the reference calls pytorch3d.ops.knn_points (:998), an un-vendored,
+# un-pinned dependency (requirements.txt:19, "git+https://github.com/facebookresearch/pytorch3d.git") that is absent here, so the
+# class cannot be imported.  knn_points' published contract -- squared Euclidean distances to the K nearest points, ascending,
+# with their indices -- is restated as an explicit distance matrix + stable sort; everything after it follows the reference's
+# statements line by line (cited).  tests/test_deform.py additionally checks the closed-form gradients csrc/warp.cu uses against
+# autograd of this restatement in float64.
+# ---------------------------------------------------------------------------------------------------------------------
+def control_node_warp_ref(x, nodes, log_radius, weight_logit, node_attrs, motion_mask=None, K=3, d_rot_as_res=True, local_frame=True):
+    import torch
+    x = x.detach()                                                        # :1196
+    n3 = nodes[..., :3].detach()                                          # :994
+    diff = x[:, None, :] - n3[None, :, :]
+    dist = ((diff * diff)[..., 0] + (diff * diff)[..., 1]) + (diff * diff)[..., 2]
+    nn_dist, nn_idx = torch.sort(dist, dim=1, stable=True)                # knn_points: ascending squared distances
+    nn_dist, nn_idx = nn_dist[:, :K], nn_idx[:, :K]
+    nn_radius = torch.exp(log_radius).reshape(-1)[nn_idx]                 # :893, :1001
+    nn_weight = torch.exp(-nn_dist / (2 * nn_radius ** 2))                # :1002
+    if weight_logit is not None:
+        nn_weight = nn_weight * torch.sigmoid(weight_logit).reshape(-1, 1)[nn_idx][..., 0]   # :897, :1004-1005
+    nn_weight = nn_weight + 1e-7                                          # :1006
+    nn_weight = nn_weight / nn_weight.sum(dim=-1, keepdim=True)           # :1007
+    mask = 1.0 if motion_mask is None else motion_mask.reshape(-1, 1)
+    rot_bias = torch.tensor([1.0, 0, 0, 0], dtype=x.dtype)
+    node_trans, node_rot, node_scale = node_attrs["d_xyz"], node_attrs["d_rotation"], node_attrs["d_scaling"]
+    if local_frame:                                                       # :1208-1214
+        q = node_attrs["local_rotation"] + rot_bias
+        r, i, j, k = torch.unbind(q, -1)
+        two_s = 2.0 / (q * q).sum(-1)
+        R = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r), two_s * (i * j + k * r),
+                         1 - two_s * (i * i + k * k), two_s * (j * k - i * r), two_s * (i * k - j * r), two_s * (j * k + i * r),
+                         1 - two_s * (i * i + j * j)), -1).reshape(-1, 3, 3)
+        nn_nodes = n3[nn_idx]
+        Ax = torch.einsum("nkab,nkb->nka", R[nn_idx], x[:, None] - nn_nodes) + nn_nodes + node_trans[nn_idx]
+        translate = (Ax * nn_weight[..., None]).sum(dim=1) - x
+    else:
+        translate = (node_trans[nn_idx] * nn_weight[..., None]).sum(dim=1)            # :1216
+    translate = translate * mask                                                        # :1217
+    if not d_rot_as_res:
+        rotation = (((node_rot + rot_bias)[nn_idx] * nn_weight[..., None]).sum(dim=1) - rot_bias) * mask + rot_bias   # :1222, :1232
+    else:
+        rotation = (node_rot[nn_idx] * nn_weight[..., None]).sum(dim=1) * mask          # :1251-1252
+    scale = (node_scale[nn_idx] * nn_weight[..., None]).sum(dim=1) * mask               # :1247 / :1253
+    return dict(d_xyz=translate, d_rotation=rotation, d_scaling=scale, nn_weight=nn_weight, nn_dist=nn_dist, nn_idx=nn_idx)

@@ -1,0 +1,199 @@
+"""Control-node warp of the deformation step (csrc/warp.cu, diff_gaussian_rasterization.deform).
+
+Oracle: oracle/g4r_oracle.py control_node_warp_ref, a torch restatement of ControlNodeWarp.forward + cal_nn_weight
+(utils/time_utils.py:1192-1275, :981-1015).  Parity against the reference class itself is UNPINNED: it needs pytorch3d
+(un-vendored, un-pinned, absent), so knn_points is restated from its published contract.  CPU: properties of the restatement and
+the closed-form gradients of csrc/warp.cu (mirrored in numpy) against autograd in float64.  GPU: the CUDA path against the
+restatement -- neighbour lists equal, outputs 1e-5, gradients 1e-4 -- over the d_rot_as_res / local_frame / K / mask variants."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.g4r_oracle import control_node_warp_ref
+
+
+def make_case(N, M, stride=3, seed=0, dtype=torch.float32, with_weight=True, with_mask=True):
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    x = rn(N, 3)
+    nodes = rn(M, stride)
+    log_radius = rn(M) * 0.3 - 0.5
+    weight_logit = rn(M, 1) if with_weight else None
+    attrs = {k: rn(M, c) * 0.3 for k, c in (("d_xyz", 3), ("d_rotation", 4), ("d_scaling", 3), ("local_rotation", 4))}
+    mask = (torch.rand(N, 1, generator=g, dtype=torch.float64) > 0.3).to(torch.float64) if with_mask else None
+    grads = (rn(N, 3), rn(N, 4), rn(N, 3))
+    cast = lambda t: None if t is None else t.to(dtype)
+    return dict(x=cast(x), nodes=cast(nodes), log_radius=cast(log_radius), weight_logit=cast(weight_logit), attrs={k: cast(v) for k, v in attrs.items()},
+                mask=cast(mask), grads=tuple(cast(t) for t in grads))
+
+
+def ref_with_grads(c, K, res, local, dtype=torch.float64):
+    cast = lambda t: None if t is None else t.detach().cpu().to(dtype)
+    lr = cast(c["log_radius"]).requires_grad_()
+    wl = cast(c["weight_logit"])
+    if wl is not None:
+        wl.requires_grad_()
+    attrs = {k: cast(v).requires_grad_() for k, v in c["attrs"].items()}
+    out = control_node_warp_ref(cast(c["x"]), cast(c["nodes"]), lr, wl, attrs, cast(c["mask"]), K, res, local)
+    gT, gR, gS = (cast(t) for t in c["grads"])
+    L = (out["d_xyz"] * gT).sum() + (out["d_rotation"] * gR).sum() + (out["d_scaling"] * gS).sum()
+    names = ["log_radius"] + (["weight_logit"] if wl is not None else []) + ["d_xyz", "d_rotation", "d_scaling"] + (["local_rotation"] if local else [])
+    params = [lr] + ([wl] if wl is not None else []) + [attrs["d_xyz"], attrs["d_rotation"], attrs["d_scaling"]] + ([attrs["local_rotation"]] if local else [])
+    return out, dict(zip(names, torch.autograd.grad(L, params)))
+
+
+def test_restatement_properties():
+    c = make_case(300, 40, stride=5, dtype=torch.float64)
+    out = control_node_warp_ref(c["x"], c["nodes"], c["log_radius"], c["weight_logit"], c["attrs"], c["mask"], 3, True, True)
+    assert torch.allclose(out["nn_weight"].sum(-1), torch.ones(300, dtype=torch.float64))
+    assert (out["nn_dist"][:, 1:] >= out["nn_dist"][:, :-1]).all()                       # ascending squared distances
+    d = ((c["x"][:, None] - c["nodes"][None, :, :3]) ** 2).sum(-1)
+    assert torch.allclose(out["nn_dist"][:, 0], d.min(1).values)
+    still = c["mask"].reshape(-1) == 0                                                    # motion_mask = 0 freezes the Gaussian
+    assert (out["d_xyz"][still] == 0).all() and (out["d_rotation"][still] == 0).all() and (out["d_scaling"][still] == 0).all()
+    # identity local rotations and one shared translation move every Gaussian by exactly that translation
+    attrs = {k: torch.zeros_like(v) for k, v in c["attrs"].items()}
+    attrs["d_xyz"] = attrs["d_xyz"] + torch.tensor([0.1, -0.2, 0.3], dtype=torch.float64)
+    out = control_node_warp_ref(c["x"], c["nodes"], c["log_radius"], c["weight_logit"], attrs, None, 3, True, True)
+    assert torch.allclose(out["d_xyz"], torch.tensor([0.1, -0.2, 0.3], dtype=torch.float64).expand(300, 3), atol=1e-12)
+
+
+@pytest.mark.parametrize("res,local", [(True, True), (True, False), (False, True), (False, False)])
+def test_closed_form_gradients_of_the_kernel_match_autograd(res, local):
+    """The backward of csrc/warp.cu, statement by statement in numpy float64, against autograd of the restatement."""
+    N, M, K = 160, 23, 3
+    c = make_case(N, M, stride=4, seed=3, dtype=torch.float64)
+    out, auto = ref_with_grads(c, K, res, local)
+    idx, d, w = out["nn_idx"].numpy(), out["nn_dist"].detach().numpy(), out["nn_weight"].detach().numpy()
+    X, n3 = c["x"].numpy(), c["nodes"][:, :3].numpy()
+    lr, wl = c["log_radius"].numpy(), c["weight_logit"].numpy().reshape(-1)
+    T, Rq, S, LQ = (c["attrs"][k].numpy() for k in ("d_xyz", "d_rotation", "d_scaling", "local_rotation"))
+    m = c["mask"].numpy().reshape(-1)
+    gT, gR, gS = (t.numpy() for t in c["grads"])
+    bias = np.array([0.0 if res else 1.0, 0, 0, 0])
+    acc = np.zeros((M, 24))
+
+    def quat_to_mat(q):
+        r, i, j, k = q
+        s2 = 2 / (q @ q)
+        return np.array([[1 - s2 * (j * j + k * k), s2 * (i * j - k * r), s2 * (i * k + j * r)], [s2 * (i * j + k * r), 1 - s2 * (i * i + k * k), s2 * (j * k - i * r)],
+                         [s2 * (i * k - j * r), s2 * (j * k + i * r), 1 - s2 * (i * i + j * j)]])
+
+    for n in range(N):
+        gt, gq, gs = gT[n] * m[n], gR[n] * m[n], gS[n] * m[n]
+        A, gw, e, sg, ir2 = 0.0, np.zeros(K), np.zeros(K), np.zeros(K), np.zeros(K)
+        for k in range(K):
+            i = idx[n, k]
+            ir2[k] = 1 / np.exp(lr[i]) ** 2
+            e[k] = np.exp(-d[n, k] * 0.5 * ir2[k])
+            sg[k] = 1 / (1 + np.exp(-wl[i]))
+            A += e[k] * sg[k] + 1e-7
+            if local:
+                ev = X[n] - n3[i]
+                g = gt @ (quat_to_mat(LQ[i] + np.array([1.0, 0, 0, 0])) @ ev + n3[i] + T[i])
+                acc[i, 10:19] += (w[n, k] * np.outer(gt, ev)).reshape(-1)
+            else:
+                g = gt @ T[i]
+            gw[k] = g + gq @ (Rq[i] + bias) + gs @ S[i]
+            acc[i, 0:3] += w[n, k] * gt
+            acc[i, 3:7] += w[n, k] * gq
+            acc[i, 7:10] += w[n, k] * gs
+        wgw = (w[n] * gw).sum()
+        for k in range(K):
+            i = idx[n, k]
+            ga = (gw[k] - wgw) / A
+            acc[i, 19] += ga * sg[k] * e[k] * d[n, k] * ir2[k]
+            acc[i, 20] += ga * e[k] * sg[k] * (1 - sg[k])
+    mine = {"log_radius": acc[:, 19], "weight_logit": acc[:, 20].reshape(M, 1), "d_xyz": acc[:, 0:3], "d_rotation": acc[:, 3:7], "d_scaling": acc[:, 7:10]}
+    if local:
+        glq = np.zeros((M, 4))
+        for i in range(M):
+            G = acc[i, 10:19]
+            q = LQ[i] + np.array([1.0, 0, 0, 0])
+            r, a, j, k = q
+            s2 = 2 / (q @ q)
+            W = (G[0] * -(j * j + k * k) + G[1] * (a * j - k * r) + G[2] * (a * k + j * r) + G[3] * (a * j + k * r) + G[4] * -(a * a + k * k) +
+                 G[5] * (j * k - a * r) + G[6] * (a * k - j * r) + G[7] * (j * k + a * r) + G[8] * -(a * a + j * j))
+            dq = np.array([-k * G[1] + j * G[2] + k * G[3] - a * G[5] - j * G[6] + a * G[7],
+                           j * (G[1] + G[3]) + k * (G[2] + G[6]) - 2 * a * (G[4] + G[8]) + r * (G[7] - G[5]),
+                           -2 * j * (G[0] + G[8]) + a * (G[1] + G[3]) + r * (G[2] - G[6]) + k * (G[5] + G[7]),
+                           -2 * k * (G[0] + G[4]) + r * (G[3] - G[1]) + a * (G[2] + G[6]) + j * (G[5] + G[7])])
+            glq[i] = s2 * dq - s2 * s2 * W * q
+        mine["local_rotation"] = glq
+    for name, g in auto.items():
+        np.testing.assert_allclose(mine[name], g.numpy(), rtol=1e-9, atol=1e-12, err_msg=name)
+
+
+def test_control_node_warp_has_no_cpu_path():
+    from diff_gaussian_rasterization.deform import control_node_warp
+    c = make_case(8, 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        control_node_warp(c["x"], c["nodes"], c["log_radius"], c["weight_logit"], c["attrs"], c["mask"])
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+def run_cuda(c, K, res, local, device):
+    from diff_gaussian_rasterization.deform import control_node_warp
+    dev = lambda t: None if t is None else t.to(device)
+    lr = dev(c["log_radius"]).requires_grad_()
+    wl = dev(c["weight_logit"])
+    if wl is not None:
+        wl.requires_grad_()
+    attrs = {k: dev(v).requires_grad_() for k, v in c["attrs"].items()}
+    out = control_node_warp(dev(c["x"]), dev(c["nodes"]), lr, wl, attrs, dev(c["mask"]), K=K, d_rot_as_res=res, local_frame=local, return_nn=True)
+    gT, gR, gS = (dev(t) for t in c["grads"])
+    ((out["d_xyz"] * gT).sum() + (out["d_rotation"] * gR).sum() + (out["d_scaling"] * gS).sum()).backward()
+    grads = {"log_radius": lr.grad, "d_xyz": attrs["d_xyz"].grad, "d_rotation": attrs["d_rotation"].grad, "d_scaling": attrs["d_scaling"].grad}
+    if wl is not None:
+        grads["weight_logit"] = wl.grad
+    if local:
+        grads["local_rotation"] = attrs["local_rotation"].grad
+    return out, grads
+
+
+def check_case(c, K, res, local, device):
+    out, grads = run_cuda(c, K, res, local, device)
+    ref32 = control_node_warp_ref(c["x"], c["nodes"], c["log_radius"], c["weight_logit"], c["attrs"], c["mask"], K, res, local)
+    assert torch.equal(out["nn_idx"].cpu(), ref32["nn_idx"]), "neighbour lists differ"
+    assert torch.equal(out["nn_dist"].cpu(), ref32["nn_dist"]), "squared distances are not bit-identical to the float32 restatement"
+    ref, auto = ref_with_grads(c, K, res, local)
+    for k in ("nn_weight", "d_xyz", "d_rotation", "d_scaling"):
+        a, b = out[k].detach().cpu().double(), ref[k].detach()
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max())), k
+    for name, g in auto.items():
+        a = grads[name].detach().cpu().double().reshape(g.shape)
+        assert float((a - g).norm() / g.norm()) < 1e-4, (name, float((a - g).norm() / g.norm()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,local", [(True, True), (True, False), (False, True), (False, False)])
+def test_cuda_matches_the_restatement(device, res, local):
+    check_case(make_case(5000, 512, stride=3, seed=1), 3, res, local, device)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [1, 2, 5, 8])
+def test_cuda_matches_the_restatement_for_every_K(device, K):
+    check_case(make_case(3000, 100, stride=5, seed=2), K, True, True, device)
+
+
+@pytest.mark.gpu
+def test_cuda_optional_inputs_and_large_node_sets(device):
+    check_case(make_case(2000, 64, seed=4, with_weight=False, with_mask=False), 3, True, True, device)
+    check_case(make_case(4000, 2500, seed=5), 3, True, True, device)        # > 2048 nodes: two staging passes, global accumulators
+    from diff_gaussian_rasterization.deform import control_node_warp
+    c = make_case(0, 16)
+    dev = lambda t: t.to(device)
+    out = control_node_warp(dev(c["x"]), dev(c["nodes"]), dev(c["log_radius"]), dev(c["weight_logit"]), {k: dev(v) for k, v in c["attrs"].items()}, None)
+    assert out["d_xyz"].shape == (0, 3) and out["d_rotation"].shape == (0, 4)
+    with pytest.raises(ValueError):
+        control_node_warp(dev(c["x"]), dev(c["nodes"]), dev(c["log_radius"]), None, {k: dev(v) for k, v in c["attrs"].items()}, None, K=9)
+
+
+@pytest.mark.gpu
+def test_warp_feeds_the_fused_rasterizer(device):
+    """The dict goes straight into render()'s dx / dr / ds (utils/slam_backend.py:361-372): shapes and dtypes line up."""
+    c = make_case(1000, 512, seed=6)
+    out, _ = run_cuda(c, 3, True, True, device)
+    assert out["d_xyz"].shape == (1000, 3) and out["d_rotation"].shape == (1000, 4) and out["d_scaling"].shape == (1000, 3)
+    assert out["d_opacity"] is None and out["d_color"] is None and out["nn_idx"].dtype == torch.int64

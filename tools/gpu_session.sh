@@ -49,6 +49,8 @@ for stage in "$@"; do
     knn)      timeout 900 python tools/knn_digests.py --write gpurun_out/knn_digests_ref.json > gpurun_out/knn_digests.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/knn_digests.log | cut -c1-400
               [ -f gpurun_out/knn_digests_ref.json ] && [ ! -f tests/golden/knn_digests_ref.json ] && cp gpurun_out/knn_digests_ref.json tests/golden/
               timeout 900 python -m pytest tests/test_knn.py -m gpu -q --timeout 600 > gpurun_out/pytest_knn.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_knn.log ;;
+    deform)   timeout 900 python -m pytest tests/test_deform.py -m gpu -q --timeout 600 > gpurun_out/pytest_deform.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_deform.log | cut -c1-300
+              timeout 600 python tools/deform_bench.py > gpurun_out/deform_bench.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/deform_bench.log ;;
     knnsan)   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/knn_digests.py K1_depthmap_20k K5_duplicates_60k > gpurun_out/knn_memcheck.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/knn_memcheck.log ;;
     digests)  timeout 900 python tools/digests.py --write gpurun_out/digests_ref.json > gpurun_out/digests.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/digests.log ;;
     shapes)   for wl in C3map track; do for impl in ours reference; do
