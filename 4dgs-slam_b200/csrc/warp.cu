@@ -262,7 +262,7 @@ static int warp_params(const G4RWarpIn* in, WarpParams* p) {
     if (in->N < 0 || in->M <= 0) return g4r_set_error(G4R_EINVAL, "N = %d, M = %d: need N >= 0 and M > 0", in->N, in->M);
     if (in->K < 1 || in->K > WARP_KMAX) return g4r_set_error(G4R_EINVAL, "K = %d is outside [1, %d]", in->K, WARP_KMAX);
     if (in->node_stride < 3) return g4r_set_error(G4R_EINVAL, "node_stride = %d < 3", in->node_stride);
-    if (!in->x || !in->nodes || !in->log_radius || !in->d_xyz || !in->d_rotation || !in->d_scaling)
+    if ((in->N > 0 && !in->x) || !in->nodes || !in->log_radius || !in->d_xyz || !in->d_rotation || !in->d_scaling)
         return g4r_set_error(G4R_EINVAL, "x, nodes, log_radius, d_xyz, d_rotation, d_scaling are required");
     if (in->local_frame && !in->local_rotation) return g4r_set_error(G4R_EINVAL, "local_frame needs local_rotation");
     p->N = in->N; p->M = in->M; p->K = in->K; p->node_stride = in->node_stride; p->d_rot_as_res = in->d_rot_as_res; p->local_frame = in->local_frame;
