@@ -1,6 +1,6 @@
 """Small forward+backward cases for compute-sanitizer (memcheck / racecheck / initcheck): the standard path on three scene
 types (SH 3; precomputed colour + covariance; oversized tiles -> global-memory radix sort), the raw-parameter path with the
-in-kernel mask and dynamic offsets, and the fused loss kernel."""
+in-kernel mask and dynamic offsets, the fused loss kernel, distCUDA2 (simple_knn drop-in) and the control-node warp."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -37,4 +37,21 @@ loss = slam_loss("tracking", color, depth, torch.rand(3, sc.H, sc.W, generator=g
 loss.backward()
 torch.cuda.synchronize()
 print("fused path loss", float(loss.detach()))
+
+from simple_knn._C import distCUDA2
+from tools import knn_cases
+for name, pts in knn_cases.random_cases(seed=5, n=3000):
+    d = distCUDA2(torch.from_numpy(pts).to(dev))
+torch.cuda.synchronize()
+print("distCUDA2 cases done", float(d[0]))
+
+from diff_gaussian_rasterization.deform import control_node_warp
+for N, M, K, local in ((3000, 512, 3, True), (1500, 2300, 5, False)):
+    x, nodes = torch.randn(N, 3, generator=g).to(dev), torch.randn(M, 5, generator=g).to(dev)
+    lr, wl = (torch.randn(M, generator=g) * 0.3 - 0.5).to(dev).requires_grad_(), torch.randn(M, 1, generator=g).to(dev).requires_grad_()
+    attrs = {k: (torch.randn(M, c, generator=g) * 0.3).to(dev).requires_grad_() for k, c in (("d_xyz", 3), ("d_rotation", 4), ("d_scaling", 3), ("local_rotation", 4))}
+    o = control_node_warp(x, nodes, lr, wl, attrs, (torch.rand(N, 1, generator=g) > 0.3).float().to(dev), K=K, local_frame=local)
+    (o["d_xyz"].sum() + o["d_rotation"].sum() + o["d_scaling"].sum()).backward()
+torch.cuda.synchronize()
+print("control_node_warp cases done", float(lr.grad.abs().sum()))
 print("sanitize cases done")
