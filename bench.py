@@ -246,6 +246,15 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
     e1.record(main)
     torch.cuda.synchronize()
     dist_barrier()
+    # the host link on its own: the same packed copy with nothing else running (tells copy-bound from kernel-bound)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(side):
+        c0.record(side)
+        for _ in range(5):
+            packs[0].copy_(wl.host_pack, non_blocking=True)
+        c1.record(side)
+    torch.cuda.synchronize()
+    wl.h2d_copy_ms_alone = c0.elapsed_time(c1) / 5
     return e0.elapsed_time(e1)
 
 
@@ -626,7 +635,9 @@ def main():
             # rate (~35-50 GB/s per PCIe gen5 x16 GPU; N ranks share the host's DRAM / root complexes) e2e is copy-bound, not
             # kernel-bound, which is what separates it from `value`.
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
-                    "h2d_gbs_per_gpu": e2e_value / world * wl.h2d_bytes / 1e9, "h2d_gbs_aggregate": e2e_value * wl.h2d_bytes / 1e9},
+                    "h2d_gbs_per_gpu": e2e_value / world * wl.h2d_bytes / 1e9, "h2d_gbs_aggregate": e2e_value * wl.h2d_bytes / 1e9,
+                    "h2d_copy_ms_alone": getattr(wl, "h2d_copy_ms_alone", None),
+                    "h2d_link_gbs_alone": (wl.h2d_bytes / 1e6 / wl.h2d_copy_ms_alone) if getattr(wl, "h2d_copy_ms_alone", None) else None},
             # launches of this library's kernels inside the timed region, counted by the library's stage profile (it covers
             # the warm-up steps too, which run the same launches)
             "gpu_launches": int(round(sum(v[1] for v in stage.values()) * args.steps / (args.steps + args.warmup))) if stage else 0,

@@ -30,7 +30,7 @@ for stage in "$@"; do
               python tools/ncu_summary.py gpurun_out/prof_all.ncu-rep "${G4R_TAG:-r01_v7}" && cp profiles/ncu_traffic.json profiles/${G4R_TAG:-r01_v7}_ncu_summary.md gpurun_out/ ;;
     sharded2) for wl in small X2 X4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py --workload $wl > gpurun_out/sharded_$wl.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_$wl.log | cut -c1-1800; done ;;
     sharded2py) for wl in small X4; do G4R_SHARD_NATIVE=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29516 tools/sharded_check.py --workload $wl --out gpurun_out/py > gpurun_out/sharded_py_$wl.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_py_$wl.log | cut -c1-1800; done ;;
-    shardedN) n=${G4R_NGPU:-8}; for wl in X4; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 tools/sharded_check.py --workload $wl > gpurun_out/sharded_${wl}_x$n.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_${wl}_x$n.log | cut -c1-2500; done ;;
+    shardedN) n=${G4R_NGPU:-8}; for wl in ${G4R_SHARD_WL:-X4}; do timeout ${G4R_TIMEOUT:-900} python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 tools/sharded_check.py --workload $wl > gpurun_out/sharded_${wl}_x$n.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/sharded_${wl}_x$n.log | cut -c1-2500; done ;;
     benchN)   n=${G4R_NGPU:-8}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $n --steps 100 > gpurun_out/bench_x$n.json 2> gpurun_out/bench_x$n.err; echo "rc=$?"; cat gpurun_out/bench_x$n.json | cut -c1-4000; tail -5 gpurun_out/bench_x$n.err ;;
     bench2)   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 100 --no-cpu-baseline > gpurun_out/bench_x2.json 2> gpurun_out/bench_x2.err; echo "rc=$?"; cat gpurun_out/bench_x2.json ;;
     shard8)   for n in 2 4 8; do

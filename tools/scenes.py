@@ -288,8 +288,13 @@ EXACT_CONFIGS = {        # BASELINE.json config sizes on the bit-reproducible ge
 }
 
 
+LARGE_CONFIGS = {        # beyond BASELINE.json: a frame large enough for the Gaussian-sharded render to pay (no reference digests)
+    "X5": dict(P=8_000_000, W=1920, H=1088, sh_degree=0),
+}
+
+
 def exact_scene(name: str, seed: int = 0) -> Scene:
-    return make_scene_exact(seed=seed, name=name, **EXACT_CONFIGS[name])
+    return make_scene_exact(seed=seed, name=name, **(EXACT_CONFIGS.get(name) or LARGE_CONFIGS[name]))
 
 
 def input_digest(sc: Scene) -> str:

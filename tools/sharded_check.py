@@ -19,8 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "4dgs-slam_b200"))
 
 def load_scene(workload, dev):
     """X* = tools.scenes.exact_scene (bit-reproducible on every rank); C* / small = rank 0's scene broadcast to all."""
-    from tools.scenes import EXACT_CONFIGS, broadcast_scene, config_scene, exact_scene, make_scene
-    if workload in EXACT_CONFIGS:
+    from tools.scenes import EXACT_CONFIGS, LARGE_CONFIGS, broadcast_scene, config_scene, exact_scene, make_scene
+    if workload in EXACT_CONFIGS or workload in LARGE_CONFIGS:
         return exact_scene(workload).to(dev)
     sc_cpu = config_scene(workload) if workload.startswith("C") else make_scene(20000, 320, 240, sh_degree=2, seed=5)
     return broadcast_scene(sc_cpu.to(dev))
