@@ -36,8 +36,6 @@ __all__ = [
     "dynamic_slots",
     "captured_overflow",
     "reset_captured",
-    "set_deferred_capacity_check",
-    "check_deferred",
 ]
 
 # ----------------------------------------------------------------------------------------------
@@ -181,74 +179,6 @@ _cap_hint: dict = {}
 
 # CUDA-graph capture: no host read-back is possible, so phase 2 gets capacity = hint x this factor.
 _GRAPH_CAPACITY_FACTOR = 2.0
-
-# Deferred capacity check (opt-in: set_deferred_capacity_check(True) or G4R_DEFERRED_CHECK=1).  The default forward blocks the
-# host until the frame's instance count N has come back (to re-run the frame if the speculative capacity was too small), which
-# also stops the host from enqueueing ahead of the GPU: a loop whose host work per frame is close to its GPU work (0.6 ms vs
-# 0.6 ms at 500 k Gaussians) then pays both.  In deferred mode phase 2 gets `factor` x the high-water mark of N -- memory is
-# not the constraint on a 180 GB part -- nothing waits, and a ring of contexts (one pinned word + event each) verifies every
-# frame a few forwards later.  An overflow is never silent: the forward kernels leave such a frame's outputs untouched, its
-# backward returns zeros, and the next forward / check_deferred() that reaches its slot raises.
-_DEFERRED = {"on": os.environ.get("G4R_DEFERRED_CHECK", "0") not in ("", "0"), "factor": 4.0}
-_RING = 4
-
-
-def set_deferred_capacity_check(on: bool, factor: float = 4.0) -> None:
-    """Turn the deferred capacity check on / off for this process (see above).  `factor` = capacity over the high-water mark
-    of num_rendered.  The first frame of a (device, resolution) always runs the blocking check (there is no history yet)."""
-    if on and factor <= 0:
-        raise ValueError("factor must be positive")
-    if not on:
-        check_deferred()
-    _DEFERRED["on"], _DEFERRED["factor"] = bool(on), float(factor)
-
-
-def _ring(device: torch.device) -> dict:
-    table = getattr(_tls, "ring", None)
-    if table is None:
-        table = _tls.ring = {}
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    r = table.get(idx)
-    if r is None:
-        ctxs = []
-        for _ in range(_RING):
-            out = ctypes.c_void_p()
-            _check(_lib.g4r_context_create(ctypes.byref(out)))
-            ctxs.append(out.value)
-        r = table[idx] = dict(ctx=ctxs, pos=0, pending=[None] * _RING)
-    return r
-
-
-def _settle(r: dict, slot: int) -> None:
-    """Verify the frame that used this slot last (blocks only if the GPU has not reached that frame's tile scan yet)."""
-    pend = r["pending"][slot]
-    if pend is None:
-        return
-    r["pending"][slot] = None
-    cap, key = pend
-    N = int(_lib.g4r_wait_num_rendered(r["ctx"][slot]))
-    if N < 0:
-        _check(N)
-    with _state_lock:
-        _cap_hint[key] = max(N, int(_cap_hint.get(key, 0) * 0.95))
-    if N > cap:
-        raise RuntimeError(f"diff_gaussian_rasterization: a frame rendered with the deferred capacity check needed {N} (tile, Gaussian) "
-                           f"instances but was given room for {cap}; its outputs were left unwritten and its gradients are zero. "
-                           "The capacity hint has been raised; re-render it, use a larger factor in set_deferred_capacity_check, "
-                           "or turn the deferred check off")
-
-
-def check_deferred() -> None:
-    """Verify every frame of the calling thread that is still unchecked (deferred capacity check); raises like the forward would."""
-    err = None
-    for r in (getattr(_tls, "ring", None) or {}).values():
-        for slot in range(_RING):
-            try:
-                _settle(r, slot)
-            except RuntimeError as e:           # settle them all, report the first
-                err = err or e
-    if err is not None:
-        raise err
 
 
 def captured_overflow(device=None) -> bool:
@@ -411,22 +341,11 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
 
     keep: list = []
     with _on_device(device):
-        key = (device.index, W, H)
-        with _state_lock:
-            hint = _cap_hint.get(key, 0)
-        capturing = torch.cuda.is_current_stream_capturing()
-        deferred = _DEFERRED["on"] and hint > 0 and not capturing
-        if deferred:
-            ring = _ring(device)
-            slot = ring["pos"]
-            ring["pos"] = (slot + 1) % _RING
-            _settle(ring, slot)                 # the frame that used this slot _RING forwards ago; raises if it overflowed
-            ctx = ring["ctx"][slot]
-        else:
-            ctx = _context(device)
+        ctx = _context(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         frame = _make_frame(rs, device, M, keep)
         g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw, extra)
+        capturing = torch.cuda.is_current_stream_capturing()
         _check(_lib.g4r_forward_project(None if capturing else ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                         radii.data_ptr(), n_touched.data_ptr(), stream))
         # three separate tensors like the reference's: views of one buffer would make an in-place operation on any of them an
@@ -436,6 +355,9 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         opacity = torch.empty((1, H, W), **f32)
         out = _ForwardOut(color.data_ptr(), depth.data_ptr(), opacity.data_ptr(), radii.data_ptr(), n_touched.data_ptr())
 
+        key = (device.index, W, H)
+        with _state_lock:
+            hint = _cap_hint.get(key, 0)
         if capturing:
             # CUDA-graph capture (torch.cuda.graph around forward + loss + backward): no host read-back is possible, so
             # phase 2 gets a generous fixed capacity derived from the eager warm-up iterations.  A replay whose instance
@@ -454,20 +376,11 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         # stream, so the device never waits for the host (the reference blocks on a cudaMemcpy instead,
         # rasterizer_impl.cu:284).  `binning` (the sorted id list) is saved for backward; `sort_scratch` (the unsorted
         # pairs, 4x larger) dies with this call -- the caching allocator recycles it stream-ordered.
-        if deferred:
-            cap = int(hint * _DEFERRED["factor"]) + 4096
-        else:
-            cap = int(max(hint, 4 * P) * 1.25) + 4096 if hint == 0 else int(hint * 1.25) + 4096
+        cap = int(max(hint, 4 * P) * 1.25) + 4096 if hint == 0 else int(hint * 1.25) + 4096
         binning = torch.empty((_lib.g4r_binning_bytes(cap),), **u8)
         sort_scratch = torch.empty((_lib.g4r_sort_scratch_bytes(cap),), **u8)
         _check(_lib.g4r_forward_render(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                        binning.data_ptr(), sort_scratch.data_ptr(), cap, ctypes.byref(out), stream))
-        if deferred:
-            ring["pending"][slot] = (cap, key)
-            if raw is not None and raw[0] is not None:
-                keep.append(raw[0])
-            state = dict(P=P, N=-1, geom=geom, img=img, binning=binning, sort_scratch=sort_scratch, capacity=cap, frame=(frame, keep))
-            return color, radii, depth, opacity, n_touched, state
         N = int(_lib.g4r_wait_num_rendered(ctx))
         if N < 0:
             _check(N)
@@ -829,15 +742,11 @@ def rasterize_gaussians_with_state(raster_settings, means3D, opacities, shs=None
     """Forward only (no autograd); returns the 5 outputs plus the saved integer state:
     ``num_rendered``, ``point_list`` (N,), ``ranges`` (tiles,2), ``n_contrib`` (H,W), ``final_T`` (H,W)."""
     e = _empty()
-    was_deferred, _DEFERRED["on"] = _DEFERRED["on"], False          # the caller wants num_rendered now: blocking check
-    try:
-        with torch.no_grad():
-            color, radii, depth, opacity, n_touched, st = _forward_impl(
-                means3D, shs if shs is not None else e, colors_precomp if colors_precomp is not None else e, opacities,
-                scales if scales is not None else e, rotations if rotations is not None else e,
-                cov3D_precomp if cov3D_precomp is not None else e, raster_settings)
-    finally:
-        _DEFERRED["on"] = was_deferred
+    with torch.no_grad():
+        color, radii, depth, opacity, n_touched, st = _forward_impl(
+            means3D, shs if shs is not None else e, colors_precomp if colors_precomp is not None else e, opacities,
+            scales if scales is not None else e, rotations if rotations is not None else e,
+            cov3D_precomp if cov3D_precomp is not None else e, raster_settings)
     H, W = int(raster_settings.image_height), int(raster_settings.image_width)
     P, N = st["P"], st["N"]
     info = dict(num_rendered=N)

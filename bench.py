@@ -230,12 +230,6 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
         wl.result_host[4:7].copy_(theta.grad, non_blocking=True)
         free[b].record(main)
 
-    # Our arm runs this leg with the deferred capacity check: the same kernels, no host wait inside the
-    # forward, every frame verified a few forwards later and once more after the loop.  The reference has no such mode.
-    deferred = hasattr(dgr, "set_deferred_capacity_check")
-    if deferred:
-        dgr.set_deferred_capacity_check(True)
-    wl.e2e_capacity_check = "deferred (4x over-provisioned, verified 4 frames later and after the loop)" if deferred else "blocking"
     for b in range(2):
         free[b].record(main)
     upload(0)
@@ -251,8 +245,6 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
         compute(i % 2)
     e1.record(main)
     torch.cuda.synchronize()
-    if deferred:
-        dgr.set_deferred_capacity_check(False)      # settles every outstanding frame; raises if one had overflowed
     dist_barrier()
     # the host link on its own: the same packed copy with nothing else running (tells copy-bound from kernel-bound)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -644,7 +636,6 @@ def main():
             # kernel-bound, which is what separates it from `value`.
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
                     "h2d_gbs_per_gpu": e2e_value / world * wl.h2d_bytes / 1e9, "h2d_gbs_aggregate": e2e_value * wl.h2d_bytes / 1e9,
-                    "capacity_check": getattr(wl, "e2e_capacity_check", None),
                     "h2d_copy_ms_alone": getattr(wl, "h2d_copy_ms_alone", None),
                     "h2d_link_gbs_alone": (wl.h2d_bytes / 1e6 / wl.h2d_copy_ms_alone) if getattr(wl, "h2d_copy_ms_alone", None) else None},
             # launches of this library's kernels inside the timed region, counted by the library's stage profile (it covers
