@@ -630,10 +630,11 @@ def main():
                                    f"num_rendered N={N}", "parallelism": f"views x{world} (independent frames per GPU, no data-path collective)",
                        "l2": "flushed between steps (256 MiB memset outside the timed events)", "timing": "CUDA events per step on the current stream, "
                        "sum over K steps, max over ranks", "api": "public GaussianRasterizer autograd API (Python -> ctypes -> C ABI)"},
-            # e2e streams the frame's 28 MB of Gaussian tensors from pinned host memory every step (double-buffered on a side
-            # stream): h2d_gbs_per_gpu = what each GPU's host link sustains at this rate; once it sits at the link's practical
-            # rate (~35-50 GB/s per PCIe gen5 x16 GPU; N ranks share the host's DRAM / root complexes) e2e is copy-bound, not
-            # kernel-bound, which is what separates it from `value`.
+            # e2e streams the frame's 28 MB of Gaussian tensors from pinned host memory every step (one packed copy,
+            # double-buffered on a side stream).  h2d_link_gbs_alone = the same copy with nothing else running: at C3 the link
+            # needs 0.51 ms per step, the kernels 0.62 ms, and the Python / autograd host work of one eager step ~0.78 ms -- the
+            # e2e loop of this arm is host-bound (the reference arm is kernel-bound at 5.3 ms); N ranks also share the host's
+            # DRAM / root complexes.
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
                     "h2d_gbs_per_gpu": e2e_value / world * wl.h2d_bytes / 1e9, "h2d_gbs_aggregate": e2e_value * wl.h2d_bytes / 1e9,
                     "h2d_copy_ms_alone": getattr(wl, "h2d_copy_ms_alone", None),
