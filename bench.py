@@ -246,6 +246,67 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
     e1.record(main)
     torch.cuda.synchronize()
     dist_barrier()
+    # informational: the same loop with the step of each buffer captured once in a CUDA graph (possible because this rasterizer
+    # never blocks the host; the reference's forward cannot be captured) -- what is left is copy / kernel time, not Python
+    wl.e2e_graph_ms = None
+    if hasattr(dgr, "captured_overflow"):
+        try:
+            def graph_step(b):
+                t = bufs[b]
+                rs = dgr.GaussianRasterizationSettings(image_height=sc.H, image_width=sc.W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=t["bg"],
+                                                       scale_modifier=sc.scale_modifier, viewmatrix=t["viewmatrix"], projmatrix=t["projmatrix"],
+                                                       projmatrix_raw=t["projmatrix_raw"], sh_degree=sc.sh_degree, campos=t["campos"],
+                                                       prefiltered=False, debug=False)
+                leaf = {k: t[k].detach().requires_grad_(True) for k in leaf_keys}
+                means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
+                theta = torch.zeros(3, device=dev, requires_grad=True)
+                rho = torch.zeros(3, device=dev, requires_grad=True)
+                color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
+                    means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], shs=leaf.get("shs"),
+                    colors_precomp=t.get("colors_precomp"), scales=leaf.get("scales"), rotations=leaf.get("rotations"),
+                    cov3D_precomp=t.get("cov3D_precomp"), theta=theta, rho=rho)
+                loss = (color * wl.grad_color).sum() + (depth * wl.grad_depth).sum()
+                grads = torch.autograd.grad(loss, list(leaf.values()) + [means2D, theta, rho])
+                wl.result_host[:1].copy_(loss.detach().reshape(1), non_blocking=True)
+                wl.result_host[1:4].copy_(grads[-1], non_blocking=True)
+                wl.result_host[4:7].copy_(grads[-2], non_blocking=True)
+                return grads
+
+            cap_stream = torch.cuda.Stream(dev)
+            cap_stream.wait_stream(main)
+            with torch.cuda.stream(cap_stream):
+                for b in range(2):
+                    graph_step(b)
+            main.wait_stream(cap_stream)
+            torch.cuda.synchronize()
+            dgr.reset_captured()
+            graphs, keep = [], []
+            for b in range(2):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    keep.append(graph_step(b))
+                graphs.append(gph)
+            torch.cuda.synchronize()
+            for b in range(2):
+                free[b].record(main)
+            upload(0)
+            for i in range(3):
+                upload((i + 1) % 2)
+                main.wait_event(ready[i % 2]); graphs[i % 2].replay(); free[i % 2].record(main)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(main)
+            for i in range(3, 3 + steps):
+                upload((i + 1) % 2)
+                main.wait_event(ready[i % 2]); graphs[i % 2].replay(); free[i % 2].record(main)
+            g1.record(main)
+            torch.cuda.synchronize()
+            if not dgr.captured_overflow():
+                wl.e2e_graph_ms = g0.elapsed_time(g1) / steps
+            dgr.reset_captured()
+            del graphs, keep
+        except Exception as exc:                     # informational leg: never take the bench line down with it
+            sys.stderr.write(f"e2e cuda-graph leg skipped: {exc!r}\n")
     # the host link on its own: the same packed copy with nothing else running (tells copy-bound from kernel-bound)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(side):
@@ -637,6 +698,9 @@ def main():
             # DRAM / root complexes.
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
                     "h2d_gbs_per_gpu": e2e_value / world * wl.h2d_bytes / 1e9, "h2d_gbs_aggregate": e2e_value * wl.h2d_bytes / 1e9,
+                    "cuda_graph_value": (world * 1000.0 / wl.e2e_graph_ms) if getattr(wl, "e2e_graph_ms", None) else None,
+                    "cuda_graph_note": "informational: the same double-buffered loop with each buffer's step captured in a CUDA graph "
+                                       "(this rank's rate x ranks); `value` above is the eager loop",
                     "h2d_copy_ms_alone": getattr(wl, "h2d_copy_ms_alone", None),
                     "h2d_link_gbs_alone": (wl.h2d_bytes / 1e6 / wl.h2d_copy_ms_alone) if getattr(wl, "h2d_copy_ms_alone", None) else None},
             # launches of this library's kernels inside the timed region, counted by the library's stage profile (it covers
