@@ -51,12 +51,19 @@ __global__ void __launch_bounds__(G4R_BLOCK) knn_bbox_kernel(int P, const float*
             mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
         }
     }
+    __shared__ float s_mn[G4R_BLOCK / 32][3], s_mx[G4R_BLOCK / 32][3];
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            atomicMax(&hdr->bb[a], ~knn_ordered(mn[a]));
-            atomicMax(&hdr->bb[3 + a], knn_ordered(mx[a]));
-        }
+        for (int a = 0; a < 3; ++a) { s_mn[threadIdx.x >> 5][a] = mn[a]; s_mx[threadIdx.x >> 5][a] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {                           // one thread per axis: 6 atomics per CTA
+        const int a = threadIdx.x;
+        float lo = s_mn[0][a], hi = s_mx[0][a];
+#pragma unroll
+        for (int w = 1; w < G4R_BLOCK / 32; ++w) { lo = fminf(lo, s_mn[w][a]); hi = fmaxf(hi, s_mx[w][a]); }
+        atomicMax(&hdr->bb[a], ~knn_ordered(lo));
+        atomicMax(&hdr->bb[3 + a], knn_ordered(hi));
     }
 }
 

@@ -313,21 +313,33 @@ KNN_HD float knn_query(const KnnIndex& ix, const KnnGrid& g, int j, KnnStats* st
         const int G = 1 << level;
         int ck[3];
         float m = FLT_MAX;                                     // distance to the nearest block face that has cells behind it
+        // per axis and offset (0, -1, +1): squared box distance in code units (shrunk by the rounding margin), the axis' share of
+        // the Morton key, and whether the cell exists -- a block cell then costs three selects, not three bit de-interleaves
+        float ad2[3][3];
+        uint64_t ek[3][3];
+        bool in[3][3];
         for (int a = 0; a < 3; ++a) {
             ck[a] = (int)(c0[a] >> shift);
             const float lo_d = Q.u[a] - (float)ck[a] * S, hi_d = (float)(ck[a] + 1) * S - Q.u[a];
             if (ck[a] >= 2) m = fminf(m, lo_d + S);
             if (ck[a] + 2 <= G - 1) m = fminf(m, hi_d + S);
+            const float dl = fmaxf(lo_d - KNN_MARGIN, 0.0f), dh = fmaxf(hi_d - KNN_MARGIN, 0.0f);
+            ad2[a][0] = 0.0f; ad2[a][1] = dl * dl; ad2[a][2] = dh * dh;
+            in[a][0] = true; in[a][1] = ck[a] >= 1; in[a][2] = ck[a] + 1 <= G - 1;
+            ek[a][0] = knn_expand21((uint32_t)ck[a]) << a;
+            ek[a][1] = knn_expand21((uint32_t)(ck[a] - 1) & 0x1fffffu) << a;
+            ek[a][2] = knn_expand21((uint32_t)(ck[a] + 1) & 0x1fffffu) << a;
         }
         Q.best[0] = Q.best[1] = Q.best[2] = FLT_MAX;
         if (st) st->rounds++;
         for (int t = 0; t < 27; ++t) {                          // offsets in the order 0, -1, +1 per axis: own cell first
-            const int ox = (t % 3 == 0) ? 0 : (t % 3 == 1 ? -1 : 1), oy = ((t / 3) % 3 == 0) ? 0 : ((t / 3) % 3 == 1 ? -1 : 1),
-                      oz = (t / 9 == 0) ? 0 : (t / 9 == 1 ? -1 : 1);
-            const int nx = ck[0] + ox, ny = ck[1] + oy, nz = ck[2] + oz;
-            if (nx < 0 || ny < 0 || nz < 0 || nx >= G || ny >= G || nz >= G) continue;
-            const uint64_t key = knn_morton((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
-            if (t > 0 && knn_box_dist2(Q, level, key) * Q.unit2 * 0.99999f > fminf(Q.best[2], Q.reject)) continue;
+            const int ix0 = t % 3, iy0 = (t / 3) % 3, iz0 = t / 9;
+#define KNN_PICK(arr, a, i) ((i) == 0 ? arr[a][0] : ((i) == 1 ? arr[a][1] : arr[a][2]))
+            if (!(KNN_PICK(in, 0, ix0) && KNN_PICK(in, 1, iy0) && KNN_PICK(in, 2, iz0))) continue;
+            const float bd2 = (KNN_PICK(ad2, 0, ix0) + KNN_PICK(ad2, 1, iy0)) + KNN_PICK(ad2, 2, iz0);
+            if (t > 0 && bd2 * Q.unit2 * 0.99999f > fminf(Q.best[2], Q.reject)) continue;
+            const uint64_t key = KNN_PICK(ek, 0, ix0) | KNN_PICK(ek, 1, iy0) | KNN_PICK(ek, 2, iz0);
+#undef KNN_PICK
             uint32_t lo, hi;
             knn_range(ix, level, key, &lo, &hi);
             if (st) st->cells++;
