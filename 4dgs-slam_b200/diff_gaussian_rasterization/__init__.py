@@ -36,6 +36,7 @@ __all__ = [
     "dynamic_slots",
     "captured_overflow",
     "reset_captured",
+    "host_backend",
 ]
 
 # ----------------------------------------------------------------------------------------------
@@ -460,8 +461,42 @@ def _backward_impl(rs, P, means3D, sh, colors_precomp, scales, rotations, cov3Ds
 # ----------------------------------------------------------------------------------------------
 # public surface (same names / order as the reference package)
 # ----------------------------------------------------------------------------------------------
+# The same op with its host side in C++ (csrc/host/g4r_torch.cpp -> _g4r_host.so, built by __graft_entry__.build_host): a
+# torch::autograd::Function over the same C ABI, ~0.15 ms less host time per fwd+bwd.  Optional: without it (or with
+# G4R_HOST=python) everything runs through the Python Function below, which stays the specification; debug=True, CUDA-graph
+# capture and every opt-in extension always do.
+_host = None
+if os.environ.get("G4R_HOST", "cpp").lower() != "python":
+    try:
+        from . import _g4r_host as _host
+        _sizes = (ctypes.c_int32 * 5)()
+        _lib.g4r_struct_sizes(_sizes)
+        if _host.abi_version() != 5 or list(_host.struct_sizes()) != list(_sizes)[:4]:
+            _host = None                       # built against another g4r.h: rebuild with __graft_entry__.build_host()
+    except ImportError:
+        _host = None
+
+
+def host_backend() -> str:
+    """"cpp" when the standard op dispatches to the C++ host extension, else "python"."""
+    return "cpp" if _host is not None else "python"
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho,
                         raster_settings):
+    rs = raster_settings
+    if (_host is not None and means3D.is_cuda and not getattr(rs, "debug", False) and not torch.cuda.is_current_stream_capturing()):
+        key = (means3D.device.index, int(rs.image_width), int(rs.image_height))
+        with _state_lock:
+            hint = _cap_hint.get(key, 0)
+        color, radii, depth, opacity, n_touched, N = _host.rasterize(
+            means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, theta, rho, rs.bg, rs.viewmatrix, rs.projmatrix,
+            rs.projmatrix_raw, rs.campos, int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
+            int(rs.sh_degree), bool(rs.prefiltered), hint)
+        if means3D.shape[0]:
+            with _state_lock:
+                _cap_hint[key] = max(N, int(_cap_hint.get(key, 0) * 0.95))
+        return color, radii, depth, opacity, n_touched
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                      theta, rho, raster_settings)
 

@@ -690,7 +690,9 @@ def main():
             "config": {"workload": f"{args.workload}: P={sc.P} Gaussians, {sc.W}x{sc.H}, SH degree {sc.sh_degree} (M={K}), fwd+bwd incl. pose grads, "
                                    f"num_rendered N={N}", "parallelism": f"views x{world} (independent frames per GPU, no data-path collective)",
                        "l2": "flushed between steps (256 MiB memset outside the timed events)", "timing": "CUDA events per step on the current stream, "
-                       "sum over K steps, max over ranks", "api": "public GaussianRasterizer autograd API (Python -> ctypes -> C ABI)"},
+                       "sum over K steps, max over ranks",
+                       "api": "public GaussianRasterizer autograd API (host side: " + (dgr.host_backend() if hasattr(dgr, "host_backend") else "reference") +
+                              " -> C ABI)" if lib is not None else "public GaussianRasterizer autograd API of the reference build"},
             # e2e streams the frame's 28 MB of Gaussian tensors from pinned host memory every step (one packed copy,
             # double-buffered on a side stream).  h2d_link_gbs_alone = the same copy with nothing else running: at C3 the link
             # needs 0.51 ms per step, the kernels 0.62 ms, and the Python / autograd host work of one eager step ~0.78 ms -- the

@@ -16,6 +16,10 @@ def pytest_configure(config):
     # without a GPU; both are no-ops when the binaries are newer than their sources, e.g. on the GPU box).
     import __graft_entry__ as ge
     ge.build_library()
+    try:
+        ge.build_host()          # optional C++ host side of the standard op; the Python path is used when it is absent
+    except Exception as exc:     # noqa: BLE001
+        sys.stderr.write(f"build_host failed ({exc!r}); tests run on the Python host path\n")
     ge.build_oracle()
 
 

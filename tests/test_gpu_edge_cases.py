@@ -213,3 +213,57 @@ def test_two_processes_share_one_gpu(device, tmp_path):
         for k in ("color", "depth", "opacity", "radii", "n_touched"):
             h.update(out[k].detach().cpu().numpy().tobytes())
     assert hashes[0] == hashes[1] == h.hexdigest()
+
+
+def test_cpp_host_path_equals_the_python_host_path(device):
+    """The standard op dispatches to the C++ host extension (csrc/host/g4r_torch.cpp) when it is built; the Python Function is the
+    specification.  Same kernels through the same C ABI, so every output and gradient must be bit-identical, for SH and
+    precomputed inputs, a pose-only backward (nothing but theta / rho asks for a gradient) and an empty model."""
+    import diff_gaussian_rasterization as dgr
+    if dgr.host_backend() != "cpp":
+        pytest.skip("_g4r_host.so not built")
+
+    def both(fn):
+        a = fn()
+        saved, dgr._host = dgr._host, None
+        try:
+            assert dgr.host_backend() == "python"
+            b = fn()
+        finally:
+            dgr._host = saved
+        return a, b
+
+    for kw in (dict(P=6000, W=160, H=128, sh_degree=2, seed=21), dict(P=3000, W=96, H=64, sh_degree=0, seed=22, colors_precomp=True, cov3D_precomp=True)):
+        sc = make_scene(**kw).to(device)
+        a, b = both(lambda: runners.run_public_api(sc, dgr))
+        for k, v in a.items():
+            if isinstance(v, torch.Tensor):
+                assert torch.equal(v, b[k]), k
+            else:
+                assert v is None and b[k] is None, k
+
+    sc = make_scene(4000, 128, 96, sh_degree=1, seed=23).to(device)
+
+    def pose_only():
+        leaf, m2d, theta, rho = _leafs(sc, device, grad=False)
+        color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(runners.settings_for(sc, dgr))(
+            means3D=leaf["means3D"], means2D=m2d.detach(), opacities=leaf["opacities"], shs=leaf["shs"], scales=leaf["scales"],
+            rotations=leaf["rotations"], theta=theta, rho=rho)
+        ((color * sc.grad_color).sum() + (depth * sc.grad_depth).sum()).backward()
+        return torch.cat([rho.grad.reshape(-1), theta.grad.reshape(-1)]), color.detach(), n_touched
+
+    a, b = both(pose_only)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+    def empty():
+        e3 = torch.zeros(0, 3, device=device, requires_grad=True)
+        out = dgr.GaussianRasterizer(runners.settings_for(sc, dgr))(
+            means3D=e3, means2D=torch.zeros(0, 3, device=device), opacities=torch.zeros(0, 1, device=device), shs=torch.zeros(0, 4, 3, device=device),
+            scales=torch.zeros(0, 3, device=device), rotations=torch.zeros(0, 4, device=device), theta=torch.zeros(3, device=device), rho=torch.zeros(3, device=device))
+        out[0].sum().backward()
+        return out[0].detach(), out[1], e3.grad
+
+    a, b = both(empty)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
