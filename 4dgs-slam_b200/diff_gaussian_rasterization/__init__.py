@@ -342,12 +342,12 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
 
     keep: list = []
     with _on_device(device):
-        ctx = _context(device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        ctx = None if capturing else _context(device)     # (creating one allocates pinned memory: not allowed while capturing)
         stream = torch.cuda.current_stream(device).cuda_stream
         frame = _make_frame(rs, device, M, keep)
         g = _make_gaussians(P, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp, raw, extra)
-        capturing = torch.cuda.is_current_stream_capturing()
-        _check(_lib.g4r_forward_project(None if capturing else ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
+        _check(_lib.g4r_forward_project(ctx, ctypes.byref(frame), ctypes.byref(g), geom.data_ptr(), img.data_ptr(),
                                         radii.data_ptr(), n_touched.data_ptr(), stream))
         # three separate tensors like the reference's: views of one buffer would make an in-place operation on any of them an
         # autograd error ("a view ... of a function that returns multiple views")

@@ -239,12 +239,28 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
     torch.cuda.synchronize()
     dist_barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    trace = os.environ.get("G4R_E2E_TRACE", "0") != "0"      # diagnostic: host seconds spent in upload() / compute() per step
+    t_up = t_co = 0.0
+    t_wall0 = time.perf_counter()
     e0.record(main)
     for i in range(warmup, warmup + steps):
-        upload((i + 1) % 2)          # the next step's inputs travel while this step computes
-        compute(i % 2)
+        if trace:
+            a = time.perf_counter()
+            upload((i + 1) % 2)
+            b_ = time.perf_counter()
+            compute(i % 2)
+            c = time.perf_counter()
+            t_up += b_ - a
+            t_co += c - b_
+        else:
+            upload((i + 1) % 2)          # the next step's inputs travel while this step computes
+            compute(i % 2)
     e1.record(main)
+    t_host = time.perf_counter() - t_wall0
     torch.cuda.synchronize()
+    if trace:
+        sys.stderr.write(f"e2e trace: host loop {1e3 * t_host / steps:.3f} ms/step (upload {1e3 * t_up / steps:.3f}, compute {1e3 * t_co / steps:.3f}); "
+                         f"device {e0.elapsed_time(e1) / steps:.3f} ms/step\n")
     dist_barrier()
     # informational: the same loop with the step of each buffer captured once in a CUDA graph (possible because this rasterizer
     # never blocks the host; the reference's forward cannot be captured) -- what is left is copy / kernel time, not Python
