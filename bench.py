@@ -208,7 +208,11 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
             packs[b].copy_(wl.host_pack, non_blocking=True)       # the step's inputs, one copy from pinned memory
             ready[b].record(side)
 
+    marks = [0.0] * 6           # G4R_E2E_TRACE: host seconds per phase of compute()
+
     def compute(b):
+        tr = os.environ.get("G4R_E2E_TRACE", "0") != "0"
+        p0 = time.perf_counter() if tr else 0.0
         main.wait_event(ready[b])
         t = bufs[b]
         rs = dgr.GaussianRasterizationSettings(image_height=sc.H, image_width=sc.W, tanfovx=sc.tanfovx, tanfovy=sc.tanfovy, bg=t["bg"],
@@ -219,16 +223,24 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
         means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
         theta = torch.zeros(3, device=dev, requires_grad=True)
         rho = torch.zeros(3, device=dev, requires_grad=True)
+        p1 = time.perf_counter() if tr else 0.0
         color, radii, depth, opacity, n_touched = dgr.GaussianRasterizer(rs)(
             means3D=leaf["means3D"], means2D=means2D, opacities=leaf["opacities"], shs=leaf.get("shs"),
             colors_precomp=t.get("colors_precomp"), scales=leaf.get("scales"), rotations=leaf.get("rotations"),
             cov3D_precomp=t.get("cov3D_precomp"), theta=theta, rho=rho)
+        p2 = time.perf_counter() if tr else 0.0
         loss = (color * wl.grad_color).sum() + (depth * wl.grad_depth).sum()
+        p3 = time.perf_counter() if tr else 0.0
         loss.backward()
+        p4 = time.perf_counter() if tr else 0.0
         wl.result_host[:1].copy_(loss.detach().reshape(1), non_blocking=True)
         wl.result_host[1:4].copy_(rho.grad, non_blocking=True)
         wl.result_host[4:7].copy_(theta.grad, non_blocking=True)
         free[b].record(main)
+        if tr:
+            p5 = time.perf_counter()
+            for k, d in enumerate((p1 - p0, p2 - p1, p3 - p2, p4 - p3, p5 - p4)):
+                marks[k] += d
 
     for b in range(2):
         free[b].record(main)
@@ -260,7 +272,8 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
     torch.cuda.synchronize()
     if trace:
         sys.stderr.write(f"e2e trace: host loop {1e3 * t_host / steps:.3f} ms/step (upload {1e3 * t_up / steps:.3f}, compute {1e3 * t_co / steps:.3f}); "
-                         f"device {e0.elapsed_time(e1) / steps:.3f} ms/step\n")
+                         f"device {e0.elapsed_time(e1) / steps:.3f} ms/step; compute phases over warm-up + steps (ms/step): "
+                         + ", ".join(f"{n} {1e3 * m / (steps + warmup):.3f}" for n, m in zip(("setup", "forward", "loss", "backward", "readback"), marks)) + "\n")
     dist_barrier()
     # informational: the same loop with the step of each buffer captured once in a CUDA graph (possible because this rasterizer
     # never blocks the host; the reference's forward cannot be captured) -- what is left is copy / kernel time, not Python

@@ -217,8 +217,9 @@ def test_two_processes_share_one_gpu(device, tmp_path):
 
 def test_cpp_host_path_equals_the_python_host_path(device):
     """The standard op dispatches to the C++ host extension (csrc/host/g4r_torch.cpp) when it is built; the Python Function is the
-    specification.  Same kernels through the same C ABI, so every output and gradient must be bit-identical, for SH and
-    precomputed inputs, a pose-only backward (nothing but theta / rho asks for a gradient) and an empty model."""
+    specification.  Same kernels through the same C ABI: outputs and integers are bit-identical, gradients agree to the run-to-run
+    noise of the backward's floating-point atomics (1e-5), for SH and precomputed inputs, a pose-only backward (nothing but
+    theta / rho asks for a gradient) and an empty model."""
     import diff_gaussian_rasterization as dgr
     if dgr.host_backend() != "cpp":
         pytest.skip("_g4r_host.so not built")
@@ -237,10 +238,12 @@ def test_cpp_host_path_equals_the_python_host_path(device):
         sc = make_scene(**kw).to(device)
         a, b = both(lambda: runners.run_public_api(sc, dgr))
         for k, v in a.items():
-            if isinstance(v, torch.Tensor):
-                assert torch.equal(v, b[k]), k
-            else:
+            if not isinstance(v, torch.Tensor):
                 assert v is None and b[k] is None, k
+            elif k.startswith("dL_"):
+                assert v.shape == b[k].shape and float((v - b[k]).norm() / b[k].norm()) < 1e-5, k
+            else:
+                assert torch.equal(v, b[k]), k
 
     sc = make_scene(4000, 128, 96, sh_degree=1, seed=23).to(device)
 
@@ -253,8 +256,7 @@ def test_cpp_host_path_equals_the_python_host_path(device):
         return torch.cat([rho.grad.reshape(-1), theta.grad.reshape(-1)]), color.detach(), n_touched
 
     a, b = both(pose_only)
-    for x, y in zip(a, b):
-        assert torch.equal(x, y)
+    assert float((a[0] - b[0]).norm() / b[0].norm()) < 1e-5 and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
 
     def empty():
         e3 = torch.zeros(0, 3, device=device, requires_grad=True)
