@@ -278,7 +278,7 @@ def run_e2e(dgr, wl: Workload, steps, warmup, dist_barrier):
     # informational: the same loop with the step of each buffer captured once in a CUDA graph (possible because this rasterizer
     # never blocks the host; the reference's forward cannot be captured) -- what is left is copy / kernel time, not Python
     wl.e2e_graph_ms = None
-    if hasattr(dgr, "captured_overflow"):
+    if hasattr(dgr, "captured_overflow") and os.environ.get("G4R_E2E_NO_GRAPH", "0") == "0":
         try:
             def graph_step(b):
                 t = bufs[b]
