@@ -64,6 +64,7 @@ void g4r_stage_end(int stage, cudaStream_t s) {
 
 struct G4RContext {
     int32_t* host_n;        // pinned: [0..3] instance count read-back, [4..4+16*16) the sharded render's count matrix
+    uint32_t* dev_n;        // the device's address of host_n[0] (mapped pinned memory; NULL if the mapping is unavailable)
     cudaEvent_t ev;
     cudaEvent_t ev_matrix;
     bool pending;
@@ -166,6 +167,8 @@ int g4r_context_create(G4RContext** out) {
         return g4r_set_error(G4R_ECUDA, "context creation failed: %s", cudaGetErrorString(e));
     }
     c->host_n[0] = 0;
+    c->dev_n = nullptr;
+    if (cudaHostGetDevicePointer((void**)&c->dev_n, c->host_n, 0) != cudaSuccess) { c->dev_n = nullptr; (void)cudaGetLastError(); }
     *out = c;
     return G4R_OK;
 }
@@ -213,9 +216,11 @@ int g4r_forward_project(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* 
     if (g->P > 0) {
         if ((rc = launch_project(*f, *g, geom, img, radii, n_touched, s)) != G4R_OK) return rc;
     }
-    if ((rc = launch_tile_scan(*f, img, s)) != G4R_OK) return rc;
+    // N reaches the host through mapped pinned memory written by the scan kernel itself (no copy in the stream); the event
+    // behind the kernel tells the host when to read it
+    if ((rc = launch_tile_scan(*f, img, s, ctx ? ctx->dev_n : nullptr)) != G4R_OK) return rc;
     if (ctx) {
-        G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (!ctx->dev_n) G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         G4R_CUDA_OK(cudaEventRecord(ctx->ev, s));
         ctx->pending = true;
         ctx->renders_since_project = 0;
@@ -229,7 +234,7 @@ int64_t g4r_wait_num_rendered(G4RContext* ctx) {
     cudaError_t e = cudaEventSynchronize(ctx->ev);
     if (e != cudaSuccess) return g4r_set_error(G4R_ECUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
     ctx->pending = false;
-    return (int64_t)(uint32_t)ctx->host_n[0];
+    return (int64_t)(uint32_t)*(volatile int32_t*)ctx->host_n;
 }
 
 int g4r_forward_render(G4RContext* ctx, const G4RFrame* f, const G4RGaussians* g, void* geom, void* img, void* binning,
@@ -334,8 +339,8 @@ int g4r_count_tiles(G4RContext* ctx, const G4RFrame* f, int32_t P_all, const int
     char* ib = (char*)img;
     G4R_CUDA_OK(cudaMemsetAsync(ib + il.header, 0, il.ranges - il.header, s));
     if (P_all > 0 && (rc = launch_count_tiles(*f, P_all, radii_all, geom_all, img, s)) != G4R_OK) return rc;
-    if ((rc = launch_tile_scan(*f, img, s)) != G4R_OK) return rc;
-    G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if ((rc = launch_tile_scan(*f, img, s, ctx->dev_n)) != G4R_OK) return rc;
+    if (!ctx->dev_n) G4R_CUDA_OK(cudaMemcpyAsync(ctx->host_n, ib + il.header, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     G4R_CUDA_OK(cudaEventRecord(ctx->ev, s));
     ctx->pending = true;
     ctx->renders_since_project = 0;

@@ -27,8 +27,12 @@
 // Also emits `order`: the tiles grouped into ORDER_BUCKETS classes of decreasing instance count (a counting sort on
 // count/max).  The per-tile kernels map blockIdx.x through it, so the hardware block scheduler starts the heaviest
 // tiles first and the light ones fill the tail (longest-processing-time-first); results do not depend on it.
+// `mirror` (may be NULL): a word of mapped pinned HOST memory that also receives N, so the host can read it after the event
+// behind this kernel without a D2H copy in the stream (a 4-byte cudaMemcpyAsync between two kernels costs the stream a copy-engine
+// round trip: ~10-18 us of idle device per frame in the profiler trace of the eager loop, tools/e2e_gaps.py).
 __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
-                                                                 uint32_t* __restrict__ header, uint32_t* __restrict__ order, int tiles) {
+                                                                 uint32_t* __restrict__ header, uint32_t* __restrict__ order, int tiles,
+                                                                 uint32_t* __restrict__ mirror) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_wmax[SCAN_THREADS / 32];
     __shared__ uint32_t s_bucket[ORDER_BUCKETS];
@@ -64,7 +68,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __res
             if (lane >= d) wi += o;
         }
         s_warp[lane] = wi - w;                  // exclusive prefix of the warp totals
-        if (lane == 31) header[0] = wi;         // N = total number of (tile, Gaussian) instances
+        if (lane == 31) {
+            header[0] = wi;                     // N = total number of (tile, Gaussian) instances
+            if (mirror) { *mirror = wi; __threadfence_system(); }
+        }
     }
     __syncthreads();
     uint32_t run = s_warp[warp] + incl - sum;
@@ -99,12 +106,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(uint32_t* __res
     }
 }
 
-int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s) {
+int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s, uint32_t* mirror) {
     const ImageLayout il(f.width, f.height);
     char* b = (char*)img;
     g4r_stage_begin(ST_TILE_SCAN, s);
     tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)(b + il.counts), (uint2*)(b + il.ranges), (uint32_t*)(b + il.header),
-                                                (uint32_t*)(b + il.order), il.tiles);
+                                                (uint32_t*)(b + il.order), il.tiles, mirror);
     g4r_stage_end(ST_TILE_SCAN, s);
     G4R_LAUNCH_OK("tile_scan_kernel");
     return G4R_OK;

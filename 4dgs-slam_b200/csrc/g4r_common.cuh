@@ -169,7 +169,7 @@ static inline TileOwner g4r_owner(const G4RFrame& f) {
 int launch_project(const G4RFrame& f, const G4RGaussians& g, void* geom, void* img, int32_t* radii, int32_t* n_touched,
                    cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
-int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s);
+int launch_tile_scan(const G4RFrame& f, void* img, cudaStream_t s, uint32_t* mirror = nullptr);
 int launch_count_tiles(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, cudaStream_t s);
 int launch_tile_rows(const G4RFrame& f, int P, const int32_t* radii, const void* geom, int32_t* rows, cudaStream_t s);
 int launch_scatter_sort(const G4RFrame& f, int P, const int32_t* radii, const void* geom, void* img, void* binning,

@@ -40,13 +40,13 @@ def main():
     ops = sorted(by_stream[main_stream], key=lambda e: e["ts"])
     # steady state: from the first composite_backward of the timed loop's 5th step on
     names = [e["name"] for e in ops]
-    starts = [i for i, n in enumerate(names) if n.startswith("project_kernel")]
+    starts = [i for i, n in enumerate(names) if "project_kernel" in n]
     ops = ops[starts[8]:starts[-2]]
-    n_steps = sum(1 for e in ops if e["name"].startswith("project_kernel"))
+    n_steps = sum(1 for e in ops if "project_kernel" in e["name"])
     span = ops[-1]["ts"] + ops[-1]["dur"] - ops[0]["ts"]
     busy = sum(e["dur"] for e in ops)
     gaps = defaultdict(lambda: [0.0, 0])
-    short = lambda n: n.split("(")[0].split("<")[0][-60:]
+    short = lambda n: n.replace("void ", "").split("(")[0].split("<")[0][-60:]
     for a, b in zip(ops, ops[1:]):
         g = b["ts"] - (a["ts"] + a["dur"])
         if g > 1.0:
