@@ -87,3 +87,27 @@ def test_layout_offsets_are_aligned_and_ordered():
         assert getattr(lay, name) % 16 == 0, name
     assert lay.bin_point_list == 0 and lay.bin_pairs == 0          # offsets inside `binning` and inside `sort_scratch`
     assert lay.img_n_contrib - lay.img_final_T >= 4 * 640 * 480
+
+
+def test_cpp_host_extension_matches_the_library():
+    """csrc/host/g4r_torch.cpp (built by __graft_entry__.build_host, optional): compiled against the same g4r.h as libg4r.so --
+    ABI version and struct sizes agree -- and it refuses CPU tensors with the same message as the Python host side."""
+    import ctypes
+
+    import torch
+
+    import diff_gaussian_rasterization as dgr
+    assert dgr.host_backend() in ("cpp", "python")
+    if dgr.host_backend() != "cpp":
+        pytest.skip("_g4r_host.so not built")
+    host = dgr._host
+    sizes = (ctypes.c_int32 * 5)()
+    dgr._lib.g4r_struct_sizes(sizes)
+    assert host.abi_version() == dgr._lib.g4r_version() == 5
+    assert list(host.struct_sizes()) == list(sizes)[:4]
+    e = torch.empty(0)
+    args = (e, e, torch.zeros(4, 1), e, e, e, e, e, torch.ones(3), torch.eye(4), torch.eye(4), torch.eye(4), torch.zeros(3), 48, 64, 0.5, 0.5, 1.0, 0, False, 0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        host.rasterize(torch.zeros(4, 3), torch.zeros(4, 3), *args)
+    with pytest.raises(RuntimeError, match=r"must have dimensions \(num_points, 3\)"):
+        host.rasterize(torch.zeros(4, 2), torch.zeros(4, 3), *args)
