@@ -124,3 +124,23 @@ def test_distCUDA2_surface(device):
     assert torch.isfinite(torch.log(torch.sqrt(torch.clamp_min(a, 1e-7)))).all()
     with pytest.raises(RuntimeError):
         distCUDA2(torch.zeros(5, 2, device=device))
+
+
+def test_host_build_of_the_search_equals_the_oracle_on_random_small_clouds():
+    """Property test: clouds of 1 .. 400 points drawn from a coarse lattice (many exact ties, duplicates, collinear and coplanar
+    sets), scaled and shifted by powers of two and by awkward factors: the search must return the oracle's bits every time."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(P=st.integers(1, 400), side=st.integers(1, 12), dims=st.integers(1, 3), seed=st.integers(0, 2 ** 31 - 1),
+           scale=st.sampled_from([1.0, 0.125, 1024.0, 0.1, 3.3e-3, 7e4]), shift=st.sampled_from([0.0, -5.0, 1000.0, 0.3]))
+    def run(P, side, dims, seed, scale, shift):
+        rng = np.random.default_rng(seed)
+        pts = np.zeros((P, 3), np.float32)
+        pts[:, :dims] = rng.integers(0, side + 1, size=(P, dims)).astype(np.float32)
+        pts = (pts * np.float32(scale) + np.float32(shift)).astype(np.float32)
+        got, _ = knn_cases.host_search(pts)
+        assert np.array_equal(bits(got), bits(g4r_oracle.knn_mean_dist2(pts)))
+
+    run()
