@@ -125,3 +125,30 @@ def test_debug_mode_writes_the_argument_snapshot_on_failure(tmp_path, monkeypatc
                                    scales=torch.ones(P, 3), rotations=torch.ones(P, 4))
     snap = torch.load(tmp_path / "snapshot_fw.dump", weights_only=False)
     assert isinstance(snap, tuple) and snap[0].shape == (P, 3)
+
+
+def test_simple_knn_drop_in_surface():
+    """`from simple_knn._C import distCUDA2` (gaussian_splatting/scene/gaussian_model.py:18) resolves to this repo's module when
+    4dgs-slam_b200 is on the path; one positional tensor argument like submodules/simple-knn/ext.cpp; no oracle on the product path."""
+    import inspect
+
+    import simple_knn._C as knn
+    import os
+    pkg = os.path.dirname(os.path.dirname(os.path.abspath(dgr.__file__)))
+    assert os.path.abspath(knn.__file__).startswith(pkg)
+    assert list(inspect.signature(knn.distCUDA2).parameters) == ["points"]
+    src = open(knn.__file__).read()
+    assert "oracle" not in src
+
+
+def test_control_node_warp_surface():
+    """The opt-in warp takes the tensors ControlNodeWarp owns (utils/time_utils.py:824-828: nodes, _node_radius, _node_weight) and the
+    node MLP's output dict, and returns the keys its forward returns (:1248-1275)."""
+    import inspect
+
+    from diff_gaussian_rasterization import deform
+    params = list(inspect.signature(deform.control_node_warp).parameters)
+    assert params[:6] == ["x", "nodes", "log_radius", "weight_logit", "node_attrs", "motion_mask"]
+    d = inspect.signature(deform.control_node_warp).parameters
+    assert d["K"].default == 3 and d["d_rot_as_res"].default is True and d["local_frame"].default is True     # arguments.py:107,118,119
+    assert "oracle" not in open(deform.__file__).read()
